@@ -1,0 +1,185 @@
+/*
+ * reyna_b200 -- C-ABI of the B200-native DGFEM assemble-and-solve path.
+ *
+ * The reference (mattevs24/reyna, pure Python) has no FFI/plugin layer: its hot path is the Python method
+ * DGFEM.dgfem() (reyna/DGFEM/two_dimensional/main.py:181-231).  This header is the seam a maintainer would bind
+ * with ctypes from that method; every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every pointer inside rb_* structs is a DEVICE pointer unless the field comment
+ *     says "host"; all buffers are caller-owned (the library allocates nothing persistent);
+ *   - every call is stream-ordered on the caller-supplied cudaStream_t (passed as void*); none synchronises
+ *     unless documented;
+ *   - return value: 0 = ok, <0 = invalid argument (RB_E_*), >0 = cudaError_t; text via reyna_b200_last_error()
+ *     (thread-local); no exception crosses the boundary;
+ *   - all floating point is IEEE binary64; indices are int32 (as in the reference's final scipy CSR).
+ *
+ * Data layout
+ *   DoF (e,k) -> e*d + k, d = (p+1)(p+2)/2, k enumerates (i,j), i+j<=p row-major
+ *   (polygonal_basis_utils.py:7-26).  The matrix is scalar CSR whose rows (e,j) hold, per neighbouring element in
+ *   ascending order (the element itself included), d consecutive columns: exactly scipy's canonical CSR of B.
+ *   Coefficient samples are "q-major": value of quadrature point q of item t at [q*n_items + t].
+ */
+#ifndef REYNA_B200_H
+#define REYNA_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_MAX_P 3            /* polynomial degrees 1..3 have register-resident kernels                      */
+#define RB_MAX_QV 16          /* (p+1)^2 volume points                                                       */
+#define RB_MAX_QE 4           /* p+1 face points                                                             */
+
+enum {
+    RB_OK = 0,
+    RB_E_ARG = -1,            /* null / inconsistent argument                                                */
+    RB_E_DEGREE = -2,         /* polynomial degree outside 1..RB_MAX_P                                       */
+    RB_E_WORKSPACE = -3,      /* workspace too small                                                         */
+    RB_E_NOCOEF = -4,         /* neither diffusion nor advection given (main.py:172-173)                     */
+    RB_E_OVERFLOW = -5        /* nnz does not fit int32                                                      */
+};
+
+/* Flat DGFEMGeometry (reyna/geometry/two_dimensional/DGFEM.py:64-86).  Elements [0,n_rows) are assembled; elements
+ * [n_rows,n_elem) are read-only ghosts (multi-GPU partitions).  Triangles belong to row elements only. */
+typedef struct {
+    int32_t n_nodes, n_elem, n_rows, n_tri, n_iface, n_bface;
+    const double  *nodes;      /* [n_nodes][2]                      geometry.nodes                           */
+    const int32_t *tri;        /* [n_tri][3]                        geometry.subtriangulation                */
+    const int32_t *tri_elem;   /* [n_tri] non-decreasing            geometry.triangle_to_polygon             */
+    const int32_t *tri_off;    /* [n_rows+1] CSR offsets of tri_elem                                         */
+    const double  *bbox;       /* [n_elem][4] xmin,xmax,ymin,ymax   geometry.elem_bounding_boxes             */
+    const double  *area;       /* [n_elem]                          geometry.areas                           */
+    const int32_t *poly_off;   /* [n_elem+1]                        ragged mesh.filtered_regions             */
+    const int32_t *poly_vtx;   /* [poly_off[n_elem]]                                                          */
+    const int32_t *iedge;      /* [n_iface][2]                      geometry.interior_edges                  */
+    const int32_t *ielem;      /* [n_iface][2] (K1,K2)              geometry.interior_edges_to_element       */
+    const double  *inorm;      /* [n_iface][2] unit, K1 -> K2       geometry.interior_normals                */
+    const int32_t *bedge;      /* [n_bface][2]                      geometry.boundary_edges                  */
+    const int32_t *belem;      /* [n_bface]                         geometry.boundary_edges_to_element       */
+    const double  *bnorm;      /* [n_bface][2] outward              geometry.boundary_normals                */
+} rb_geom;
+
+/* Reference quadrature (HOST arrays; DGFEM._intialise_quadrature, main.py:233-257). */
+typedef struct {
+    int32_t p;                 /* polynomial degree                                                          */
+    double wv[RB_MAX_QV];      /* triangle weights (sum 4)                                                   */
+    double rv[RB_MAX_QV][2];   /* unit-triangle points                                                       */
+    double we[RB_MAX_QE];      /* Gauss-Legendre weights on [-1,1]                                           */
+    double xe[RB_MAX_QE];      /* Gauss-Legendre nodes                                                       */
+} rb_quad;
+
+/* Batched coefficient samples, evaluated ONCE by the caller on the quadrature points (replaces the per-item calls
+ * in full_assembly.py:57,65,69,73,140,159,194-195 and boundary_assembly.py:44-45,103,111-112).  NULL <=> the
+ * coefficient is None. */
+typedef struct {
+    const double *vol_a;       /* [Qv][n_tri][2][2]  diffusion at volume points                               */
+    const double *vol_b;       /* [Qv][n_tri][2]     advection                                                */
+    const double *vol_c;       /* [Qv][n_tri]        reaction                                                 */
+    const double *vol_f;       /* [Qv][n_tri]        forcing                                                  */
+    const double *if_a;        /* [Qe][n_iface][2][2]                                                         */
+    const double *if_b;        /* [Qe][n_iface][2]                                                            */
+    const double *if_a_mid;    /* [n_iface][2][2]    diffusion at the edge midpoint                           */
+    const uint8_t *if_upwind;  /* [n_iface] 1 <=> b(mid).n >= 1e-12, K1 is upwind (full_assembly.py:194)      */
+    const double *bf_a;        /* [Qe][n_bface][2][2]                                                         */
+    const double *bf_b;        /* [Qe][n_bface][2]                                                            */
+    const double *bf_g;        /* [Qe][n_bface]      Dirichlet data                                           */
+    const double *bf_a_mid;    /* [n_bface][2][2]                                                             */
+} rb_coefs;
+
+/* Block structure of B (replaces scipy's COO->CSR sort, main.py:319-320,371-372).  Built by
+ * reyna_b200_structure(); all arrays caller-allocated. */
+typedef struct {
+    int32_t *adj_off;          /* [n_rows+1]   contributing (face,side) items per row element                 */
+    int32_t *adj_item;         /* [<=2*n_iface] item = face*2+side, sorted by (neighbour, face); bit31 = same
+                                  neighbour as the previous item (merged block)                              */
+    int32_t *grp_off;          /* [n_rows+1]   distinct neighbours per row element (== adj_off without dups)  */
+    int32_t *counts;           /* [4] device scratch: n_items, n_groups, n_dup_items, max_items_per_element   */
+    int32_t n_items, n_groups, n_dup_items, max_items;   /* host copies, filled by reyna_b200_structure()     */
+} rb_structure;
+
+size_t reyna_b200_structure_workspace(int32_t n_rows, int32_t n_iface);
+
+/* Element -> face adjacency and block-row layout.  has_diffusion != 0: every interior face contributes rows to both
+ * of its elements; otherwise only to the downwind element chosen by coefs->if_upwind (the reference leaves the
+ * other half of the 2d x 2d face matrix exactly zero and scipy prunes it, main.py:211 + full_assembly.py:209-212). */
+/* Synchronises the stream once, to return the four counters in *s (the caller sizes the CSR arrays from them). */
+int reyna_b200_structure(const rb_geom *g, int has_diffusion, const uint8_t *if_upwind, rb_structure *s,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* CSR index arrays of the structural pattern: indptr [n_rows*d+1], indices [nnz] (nnz = d*d*(n_rows+n_groups)). */
+int reyna_b200_csr_pattern(const rb_geom *g, const rb_structure *s, int p, int32_t *indptr, int32_t *indices,
+                           void *stream);
+
+/* Volume + interior-face terms, summed per element in a fixed order and written straight into the CSR value array
+ * (replaces DGFEM._stiffness_matrix + localstiff, main.py:275-327 / full_assembly.py:9-77, and
+ * DGFEM._interior_stiffness_matrix + int_localstiff, main.py:329-374 / full_assembly.py:80-214).
+ * data [nnz], load [n_rows*d]; *zero_count (device int64, caller-zeroed) receives the number of exact zeros written. */
+int reyna_b200_assemble(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
+                        double sigma_D, double *data, double *load, long long *zero_count, void *stream);
+
+/* Boundary faces: elliptic (Dirichlet SIPG) and inflow terms subtracted in place from the diagonal blocks and the
+ * load (replaces _diffusion_bcs_contribution / _advection_bcs_contribution, main.py:376-474, and
+ * boundary_assembly.py:9-137).  bnd_elem [n_bnd] = elements owning boundary faces, bnd_off [n_bnd+1] and bnd_face
+ * list their boundary faces (ascending); flags[f] bit0 = elliptic, bit1 = inflow (boundary_information.py:76-91);
+ * bit2 = "matrix part goes to B[0,0]" (the reference's index quirk, main.py:397-400); spill [n_bnd] receives those sums. */
+int reyna_b200_boundary(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
+                        double sigma_D, int32_t n_bnd, const int32_t *bnd_elem, const int32_t *bnd_off,
+                        const int32_t *bnd_face, const uint8_t *flags, double *data, double *load, double *spill,
+                        long long *zero_count, void *stream);
+
+/* scipy's value-dependent pruning (csr_plus_csr / csr_minus_csr drop exact zeros, main.py:211-225): two passes.
+ * pass 1 writes row_nnz [n+1]-shaped exclusive scan into out_indptr and the total into *nnz_out (device);
+ * pass 2 copies the survivors.  Only needed when zero_count != 0. */
+size_t reyna_b200_compact_workspace(int32_t n_scalar_rows);
+int reyna_b200_compact_count(int32_t n_scalar_rows, const int32_t *indptr, const double *data, int32_t *out_indptr,
+                             void *workspace, size_t workspace_bytes, void *stream);
+int reyna_b200_compact_fill(int32_t n_scalar_rows, const int32_t *indptr, const int32_t *indices, const double *data,
+                            const int32_t *out_indptr, int32_t *out_indices, double *out_data, void *stream);
+
+/* Krylov solve replacing scipy.sparse.linalg.spsolve (main.py:231).  Block-Jacobi (d x d diagonal blocks)
+ * preconditioned CG (method 0, symmetric) or BiCGStab (method 1).  The matrix is the block-structured CSR produced
+ * above (blocked != 0) or any scalar CSR (blocked == 0, e.g. after compaction).  n_ghost extra vector entries
+ * follow the n owned ones in x; when halo != NULL it is called back (host function) before every SpMV to refresh
+ * them and to all-reduce dot products (multi-GPU); NULL for a single GPU. */
+typedef struct {
+    int32_t method;            /* 0 = CG, 1 = BiCGStab                                                       */
+    int32_t max_iter;
+    double  rtol;              /* on ||r||_2 / ||b||_2 (preconditioned recurrence, verified on the true one) */
+    int32_t check_every;       /* iterations between host convergence checks                                 */
+} rb_solve_opts;
+
+typedef struct {
+    int32_t iterations;
+    double  rel_residual;      /* true residual ||b - A x|| / ||b|| at exit                                   */
+    int32_t converged;
+} rb_solve_info;
+
+typedef int (*rb_halo_fn)(void *user, double *x_dev, void *stream);          /* refresh ghosts of x            */
+typedef int (*rb_allreduce_fn)(void *user, double *vals_dev, int n, void *stream);   /* in-place sum           */
+
+size_t reyna_b200_solve_workspace(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d);
+int reyna_b200_solve(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d, int blocked,
+                     const int32_t *indptr, const int32_t *indices, const double *data,
+                     const double *rhs, double *x, const rb_solve_opts *opts, rb_solve_info *info,
+                     rb_halo_fn halo, rb_allreduce_fn allreduce, void *user,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* y = A x on the same matrix formats (exposed for tests and for the roofline measurement of the SpMV). */
+int reyna_b200_spmv(int32_t n_rows_scalar, int32_t d, int blocked, const int32_t *indptr, const int32_t *indices,
+                    const double *data, const double *x, double *y, void *stream);
+
+/* FP64 FMA micro-benchmark used as the compute roofline denominator: runs `iters` dependent-chain FMAs on every
+ * lane of a full grid and returns the flop count through *flops (host). */
+int reyna_b200_fma_probe(int iters, double *scratch_dev, double *flops, void *stream);
+
+const char *reyna_b200_last_error(void);
+const char *reyna_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REYNA_B200_H */

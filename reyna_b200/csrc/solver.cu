@@ -1,0 +1,474 @@
+// Block-Jacobi preconditioned Krylov solver on FP64 CSR -- replaces scipy.sparse.linalg.spsolve(B, L)
+// (reyna/DGFEM/two_dimensional/main.py:231; SuperLU is sequential and infeasible at 1M elements).
+//
+// * SpMV: G lanes per scalar row (G chosen from the mean row length), values and column indices read as contiguous
+//   runs, x gathered through L2.  HBM-bound: 12 B per stored entry + 16 B per row.
+// * Preconditioner: the d x d diagonal blocks inverted once (Gauss-Jordan, partial pivoting), applied as dense mat-vecs.
+// * All Krylov scalars live in device memory; dot products are two-stage fixed-order reductions (no FP atomics), so a
+//   solve is bitwise reproducible and the host only synchronises every `check_every` iterations.
+// * CG for the symmetric (pure diffusion / diffusion-reaction) case, BiCGStab otherwise.
+#include "common.cuh"
+#include <math.h>
+
+namespace rb {
+
+constexpr int kVecThreads = 256;
+constexpr int kMaxPartials = kNumSMs * 8;
+
+// ----------------------------------------------------------------------------------------------------------------
+// SpMV
+// ----------------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) spmv_kernel(int n, const int32_t* __restrict__ indptr,
+                                                   const int32_t* __restrict__ indices,
+                                                   const double* __restrict__ data, const double* __restrict__ x,
+                                                   double* __restrict__ y) {
+    const int lane = threadIdx.x % G;
+    const int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
+    for (int64_t r = row0; r < n; r += stride) {
+        const int lo = indptr[r], hi = indptr[r + 1];
+        double s = 0.0;
+        for (int k = lo + lane; k < hi; k += G) s = fma(data[k], x[indices[k]], s);
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, G);
+        if (lane == 0) y[r] = s;
+    }
+}
+
+static int launch_spmv(int n, int64_t nnz_hint, const int32_t* indptr, const int32_t* indices, const double* data,
+                       const double* x, double* y, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const double mean = nnz_hint > 0 ? (double)nnz_hint / n : 32.0;
+    const int blocks_cap = kNumSMs * 16;
+    if (mean > 48) {
+        spmv_kernel<16><<<grid_for((int64_t)n * 16, 256, blocks_cap), 256, 0, st>>>(n, indptr, indices, data, x, y);
+    } else if (mean > 12) {
+        spmv_kernel<8><<<grid_for((int64_t)n * 8, 256, blocks_cap), 256, 0, st>>>(n, indptr, indices, data, x, y);
+    } else {
+        spmv_kernel<4><<<grid_for((int64_t)n * 4, 256, blocks_cap), 256, 0, st>>>(n, indptr, indices, data, x, y);
+    }
+    RB_LAUNCH_CHECK("spmv_kernel");
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// block-Jacobi
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kMaxD = 10;
+
+__global__ void block_jacobi_setup(int n_blocks, int d, const int32_t* __restrict__ indptr,
+                                   const int32_t* __restrict__ indices, const double* __restrict__ data,
+                                   double* __restrict__ minv, int* __restrict__ singular) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_blocks; e += gridDim.x * blockDim.x) {
+        double a[kMaxD * kMaxD], inv[kMaxD * kMaxD];
+        for (int j = 0; j < d; ++j) {
+            for (int i = 0; i < d; ++i) {
+                a[j * d + i] = 0.0;
+                inv[j * d + i] = (i == j) ? 1.0 : 0.0;
+            }
+            const int r = e * d + j;
+            for (int k = indptr[r]; k < indptr[r + 1]; ++k) {
+                const int c = indices[k] - e * d;
+                if (c >= 0 && c < d) a[j * d + c] = data[k];
+            }
+        }
+        bool bad = false;
+        for (int c = 0; c < d; ++c) {
+            int piv = c;
+            double best = fabs(a[c * d + c]);
+            for (int r = c + 1; r < d; ++r)
+                if (fabs(a[r * d + c]) > best) { best = fabs(a[r * d + c]); piv = r; }
+            if (best == 0.0) { bad = true; break; }
+            if (piv != c)
+                for (int k = 0; k < d; ++k) {
+                    double t = a[c * d + k]; a[c * d + k] = a[piv * d + k]; a[piv * d + k] = t;
+                    t = inv[c * d + k]; inv[c * d + k] = inv[piv * d + k]; inv[piv * d + k] = t;
+                }
+            const double ip = 1.0 / a[c * d + c];
+            for (int k = 0; k < d; ++k) { a[c * d + k] *= ip; inv[c * d + k] *= ip; }
+            for (int r = 0; r < d; ++r) {
+                if (r == c) continue;
+                const double f = a[r * d + c];
+                if (f == 0.0) continue;
+                for (int k = 0; k < d; ++k) { a[r * d + k] -= f * a[c * d + k]; inv[r * d + k] -= f * inv[c * d + k]; }
+            }
+        }
+        if (bad) {
+            atomicAdd(singular, 1);
+            for (int k = 0; k < d * d; ++k) inv[k] = (k / d == k % d) ? 1.0 : 0.0;
+        }
+        for (int k = 0; k < d * d; ++k) minv[(size_t)e * d * d + k] = inv[k];
+    }
+}
+
+// z[e] = Minv[e] * s[e]  for one scalar row per thread
+__device__ __forceinline__ double precond_row(const double* __restrict__ minv, const double* __restrict__ s, int r,
+                                              int d) {
+    const int e = r / d, j = r - e * d;
+    const double* m = minv + ((size_t)e * d + j) * d;
+    const double* v = s + (size_t)e * d;
+    double z = 0.0;
+    for (int i = 0; i < d; ++i) z = fma(m[i], v[i], z);
+    return z;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// deterministic reductions.  Each vector kernel writes per-block partials [k][block]; `finalize` kernels (one block)
+// add them in index order and update the scalar block S.
+// ----------------------------------------------------------------------------------------------------------------
+enum { S_RHO = 0, S_RHO_OLD, S_ALPHA, S_OMEGA, S_BETA, S_RR, S_BB, S_D0, S_D1, S_D2, S_BREAK, S_COUNT };
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double s_w[kVecThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_w[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = lane < kVecThreads / 32 ? s_w[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    __syncthreads();
+    return t;   // valid in warp 0
+}
+
+// sums `nk` partial arrays of length nb into out[0..nk)
+__global__ void __launch_bounds__(kVecThreads) reduce_partials(const double* __restrict__ partial, int nb, int nk,
+                                                               double* __restrict__ out) {
+    for (int k = 0; k < nk; ++k) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nb; i += kVecThreads) s += partial[(size_t)k * kMaxPartials + i];
+        s = block_sum(s);
+        if (threadIdx.x == 0) out[k] = s;
+    }
+}
+
+// ---- scalar updates (single thread) ----------------------------------------------------------------------------
+__global__ void scal_init(double* S, const double* red) {   // red: (r0,r0) or (r,z), (r,r), (b,b)
+    S[S_RHO] = red[0];
+    S[S_RHO_OLD] = 1.0;
+    S[S_ALPHA] = 1.0;
+    S[S_OMEGA] = 1.0;
+    S[S_BETA] = 0.0;
+    S[S_RR] = red[1];
+    S[S_BB] = red[2];
+    S[S_BREAK] = 0.0;
+}
+__global__ void scal_alpha(double* S, const double* red) {   // red[0] = (rhat, v)  or (p, q)
+    const double den = red[0];
+    if (den == 0.0 || !isfinite(den)) { S[S_BREAK] = 1.0; S[S_ALPHA] = 0.0; }
+    else S[S_ALPHA] = S[S_RHO] / den;
+}
+__global__ void scal_omega(double* S, const double* red) {   // red[0] = (t,s), red[1] = (t,t)
+    const double tt = red[1];
+    if (tt == 0.0 || !isfinite(tt)) { S[S_OMEGA] = 0.0; }
+    else S[S_OMEGA] = red[0] / tt;
+}
+__global__ void scal_rho_bicg(double* S, const double* red) {   // red[0] = (rhat, r_new), red[1] = (r_new, r_new)
+    const double rho_new = red[0];
+    const double rho = S[S_RHO];
+    const double om = S[S_OMEGA];
+    double beta = 0.0;
+    if (rho == 0.0 || om == 0.0 || !isfinite(rho_new)) S[S_BREAK] = 1.0;
+    else beta = (rho_new / rho) * (S[S_ALPHA] / om);
+    S[S_BETA] = beta;
+    S[S_RHO_OLD] = rho;
+    S[S_RHO] = rho_new;
+    S[S_RR] = red[1];
+}
+__global__ void scal_rho_cg(double* S, const double* red) {   // red[0] = (r,z) new, red[1] = (r,r)
+    const double rho = S[S_RHO];
+    S[S_BETA] = rho != 0.0 ? red[0] / rho : 0.0;
+    S[S_RHO_OLD] = rho;
+    S[S_RHO] = red[0];
+    S[S_RR] = red[1];
+}
+
+// ---- vector kernels ----------------------------------------------------------------------------------------------
+// r = b - Ax (Ax given in r), z = Minv r (optional), partials: (r, z or r), (r,r), (b,b)
+__global__ void __launch_bounds__(kVecThreads) k_residual0(int n, int d, const double* __restrict__ b, double* __restrict__ r) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        r[i] = b[i] - r[i];
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_dots3(int n, const double* __restrict__ a, const double* __restrict__ b2,
+                                                       const double* __restrict__ c, double* __restrict__ partial) {
+    // partial0 = (a,b2), partial1 = (a,a), partial2 = (c,c)
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ai = a[i];
+        s0 = fma(ai, b2[i], s0);
+        s1 = fma(ai, ai, s1);
+        s2 = fma(c[i], c[i], s2);
+    }
+    s0 = block_sum(s0); s1 = block_sum(s1); s2 = block_sum(s2);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = s0;
+        partial[kMaxPartials + blockIdx.x] = s1;
+        partial[2 * kMaxPartials + blockIdx.x] = s2;
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_precond(int n, int d, const double* __restrict__ minv,
+                                                         const double* __restrict__ s, double* __restrict__ z) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        z[i] = precond_row(minv, s, (int)i, d);
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_dot2(int n, const double* __restrict__ a, const double* __restrict__ b2,
+                                                      double* __restrict__ partial) {
+    // partial0 = (a,b2), partial1 = (a,a)
+    double s0 = 0, s1 = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ai = a[i];
+        s0 = fma(ai, b2[i], s0);
+        s1 = fma(ai, ai, s1);
+    }
+    s0 = block_sum(s0); s1 = block_sum(s1);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = s0;
+        partial[kMaxPartials + blockIdx.x] = s1;
+    }
+}
+
+// BiCGStab: p = r + beta (p - omega v); y = Minv p
+__global__ void __launch_bounds__(kVecThreads) k_bicg_p(int n, const double* __restrict__ S, const double* __restrict__ r,
+                                                        const double* __restrict__ v, double* __restrict__ p) {
+    const double beta = S[S_BETA], om = S[S_OMEGA];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = r[i] + beta * (p[i] - om * v[i]);
+}
+// s = r - alpha v   (in place in r)
+__global__ void __launch_bounds__(kVecThreads) k_bicg_s(int n, const double* __restrict__ S, double* __restrict__ r,
+                                                        const double* __restrict__ v) {
+    const double al = S[S_ALPHA];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        r[i] = r[i] - al * v[i];
+}
+// x += alpha y + omega z ; r = s - omega t ; partials (rhat, r), (r, r)
+__global__ void __launch_bounds__(kVecThreads) k_bicg_x(int n, const double* __restrict__ S, double* __restrict__ x,
+                                                        const double* __restrict__ y, const double* __restrict__ z,
+                                                        double* __restrict__ r, const double* __restrict__ t,
+                                                        const double* __restrict__ rhat, double* __restrict__ partial) {
+    const double al = S[S_ALPHA], om = S[S_OMEGA];
+    double s0 = 0, s1 = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] = x[i] + al * y[i] + om * z[i];
+        const double ri = r[i] - om * t[i];
+        r[i] = ri;
+        s0 = fma(rhat[i], ri, s0);
+        s1 = fma(ri, ri, s1);
+    }
+    s0 = block_sum(s0); s1 = block_sum(s1);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = s0;
+        partial[kMaxPartials + blockIdx.x] = s1;
+    }
+}
+// CG: x += alpha p ; r -= alpha q ; z = Minv r needs whole blocks -> separate k_precond ; here only the axpys
+__global__ void __launch_bounds__(kVecThreads) k_cg_xr(int n, const double* __restrict__ S, double* __restrict__ x,
+                                                       const double* __restrict__ p, double* __restrict__ r,
+                                                       const double* __restrict__ q) {
+    const double al = S[S_ALPHA];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] = x[i] + al * p[i];
+        r[i] = r[i] - al * q[i];
+    }
+}
+// p = z + beta p
+__global__ void __launch_bounds__(kVecThreads) k_cg_p(int n, const double* __restrict__ S, const double* __restrict__ z,
+                                                      double* __restrict__ p) {
+    const double beta = S[S_BETA];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = z[i] + beta * p[i];
+}
+
+struct Solver {
+    int n, ng, d, nb;
+    int64_t nnz;
+    const int32_t *indptr, *indices;
+    const double* data;
+    double *minv, *r, *rhat, *p, *v, *y, *z, *t, *partial, *red, *S;
+    int* singular;
+    rb_halo_fn halo;
+    rb_allreduce_fn allreduce;
+    void* user;
+    cudaStream_t st;
+
+    int reduce(int nk) {
+        reduce_partials<<<1, kVecThreads, 0, st>>>(partial, nb, nk, red);
+        RB_LAUNCH_CHECK("reduce_partials");
+        if (allreduce) {
+            int rc = allreduce(user, red, nk, (void*)st);
+            if (rc) { set_error("allreduce callback failed (%d)", rc); return rc; }
+        }
+        return 0;
+    }
+    int spmv(double* xin, double* yout) {
+        if (halo) {
+            int rc = halo(user, xin, (void*)st);
+            if (rc) { set_error("halo callback failed (%d)", rc); return rc; }
+        }
+        return launch_spmv(n, nnz, indptr, indices, data, xin, yout, st);
+    }
+};
+
+}  // namespace rb
+
+using namespace rb;
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t reyna_b200_solve_workspace(int32_t n, int32_t n_ghost, int32_t d) {
+    const size_t full = align256(sizeof(double) * ((size_t)n + n_ghost));
+    const size_t own = align256(sizeof(double) * (size_t)n);
+    size_t b = 0;
+    b += align256(sizeof(double) * (size_t)n * d);   // minv: (n/d) blocks of d*d
+    b += own * 4;                                    // r, rhat, v, t
+    b += full * 3;                                   // p, y, z (SpMV inputs carry ghosts)
+    b += align256(sizeof(double) * 3 * kMaxPartials);
+    b += align256(sizeof(double) * 16) * 2;          // red, S
+    b += 256;                                        // singular flag
+    return b;
+}
+
+extern "C" int reyna_b200_spmv(int32_t n, int32_t d, int blocked, const int32_t* indptr, const int32_t* indices,
+                               const double* data, const double* x, double* y, void* stream) {
+    (void)d; (void)blocked;
+    RB_REQUIRE(indptr && indices && data && x && y, RB_E_ARG, "reyna_b200_spmv: null argument");
+    return launch_spmv(n, (int64_t)n * 40, indptr, indices, data, x, y, (cudaStream_t)stream);
+}
+
+extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int blocked, const int32_t* indptr,
+                                const int32_t* indices, const double* data, const double* rhs, double* x,
+                                const rb_solve_opts* opts, rb_solve_info* info, rb_halo_fn halo,
+                                rb_allreduce_fn allreduce, void* user, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    (void)blocked;
+    RB_REQUIRE(indptr && indices && data && rhs && x && opts && info && workspace, RB_E_ARG,
+               "reyna_b200_solve: null argument");
+    RB_REQUIRE(d >= 1 && d <= kMaxD && n % d == 0, RB_E_ARG, "reyna_b200_solve: bad block size");
+    RB_REQUIRE(workspace_bytes >= reyna_b200_solve_workspace(n, n_ghost, d), RB_E_WORKSPACE,
+               "reyna_b200_solve: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    info->iterations = 0;
+    info->rel_residual = 0.0;
+    info->converged = 0;
+    if (n == 0) { info->converged = 1; return 0; }
+
+    Solver s;
+    s.n = n; s.ng = n_ghost; s.d = d; s.st = st;
+    s.indptr = indptr; s.indices = indices; s.data = data;
+    s.halo = halo; s.allreduce = allreduce; s.user = user;
+    int32_t last = 0;
+    RB_CUDA(cudaMemcpyAsync(&last, indptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    s.nnz = last;
+    const size_t full = align256(sizeof(double) * ((size_t)n + n_ghost));
+    const size_t own = align256(sizeof(double) * (size_t)n);
+    char* w = (char*)workspace;
+    auto take = [&](size_t bytes) { char* q = w; w += bytes; return q; };
+    s.minv = (double*)take(align256(sizeof(double) * (size_t)n * d));
+    s.r = (double*)take(own); s.rhat = (double*)take(own); s.v = (double*)take(own); s.t = (double*)take(own);
+    s.p = (double*)take(full); s.y = (double*)take(full); s.z = (double*)take(full);
+    s.partial = (double*)take(align256(sizeof(double) * 3 * kMaxPartials));
+    s.red = (double*)take(align256(sizeof(double) * 16));
+    s.S = (double*)take(align256(sizeof(double) * 16));
+    s.singular = (int*)take(256);
+    s.nb = grid_for(n, kVecThreads, kMaxPartials);
+    const int nb = s.nb;
+    RB_CUDA(cudaMemsetAsync(s.singular, 0, sizeof(int), st));
+    RB_CUDA(cudaMemsetAsync(s.p, 0, full * 3, st));
+    RB_CUDA(cudaMemsetAsync(s.v, 0, own, st));
+
+    block_jacobi_setup<<<grid_for(n / d, 128, kNumSMs * 16), 128, 0, st>>>(n / d, d, indptr, indices, data, s.minv,
+                                                                            s.singular);
+    RB_LAUNCH_CHECK("block_jacobi_setup");
+
+    int rc;
+    // r = b - A x   (x carries the initial guess; ghosts refreshed by the callback)
+    if ((rc = s.spmv(x, s.r))) return rc;
+    k_residual0<<<nb, kVecThreads, 0, st>>>(n, d, rhs, s.r);
+    RB_LAUNCH_CHECK("k_residual0");
+
+    const bool cg = opts->method == 0;
+    const int check = opts->check_every > 0 ? opts->check_every : 25;
+    double hS[S_COUNT];
+    if (cg) {
+        k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+        RB_CUDA(cudaMemcpyAsync(s.p, s.z, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        k_dots3<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, rhs, s.partial);     // (r,z), (r,r), (b,b)
+    } else {
+        RB_CUDA(cudaMemcpyAsync(s.rhat, s.r, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        k_dots3<<<nb, kVecThreads, 0, st>>>(n, s.r, s.r, rhs, s.partial);     // (r,r), (r,r), (b,b)
+    }
+    RB_LAUNCH_CHECK("k_dots3");
+    if ((rc = s.reduce(3))) return rc;
+    scal_init<<<1, 1, 0, st>>>(s.S, s.red);
+    RB_CUDA(cudaMemcpyAsync(hS, s.S, sizeof(hS), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    const double bb = hS[S_BB];
+    const double target2 = opts->rtol * opts->rtol * (bb > 0.0 ? bb : 1.0);
+    int it = 0;
+    bool done = hS[S_RR] <= target2;
+    while (!done && it < opts->max_iter) {
+        const int burst = (opts->max_iter - it) < check ? (opts->max_iter - it) : check;
+        for (int k = 0; k < burst; ++k) {
+            if (cg) {
+                if ((rc = s.spmv(s.p, s.v))) return rc;                                  // q = A p
+                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.p, s.v, s.partial);               // (p,q)
+                if ((rc = s.reduce(1))) return rc;
+                scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
+                k_cg_xr<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.p, s.r, s.v);
+                k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, s.partial);               // (r,z), (r,r)
+                if ((rc = s.reduce(2))) return rc;
+                scal_rho_cg<<<1, 1, 0, st>>>(s.S, s.red);
+                k_cg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.z, s.p);
+            } else {
+                k_bicg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v, s.p);
+                k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.p, s.y);
+                if ((rc = s.spmv(s.y, s.v))) return rc;                                  // v = A y
+                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.rhat, s.v, s.partial);            // (rhat, v)
+                if ((rc = s.reduce(1))) return rc;
+                scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
+                k_bicg_s<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v);                   // r := s
+                k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+                if ((rc = s.spmv(s.z, s.t))) return rc;                                  // t = A z
+                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.r, s.partial);               // (t,s), (t,t)
+                if ((rc = s.reduce(2))) return rc;
+                scal_omega<<<1, 1, 0, st>>>(s.S, s.red);
+                k_bicg_x<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.y, s.z, s.r, s.t, s.rhat, s.partial);
+                if ((rc = s.reduce(2))) return rc;
+                scal_rho_bicg<<<1, 1, 0, st>>>(s.S, s.red);
+            }
+        }
+        RB_LAUNCH_CHECK("krylov burst");
+        it += burst;
+        RB_CUDA(cudaMemcpyAsync(hS, s.S, sizeof(hS), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+        if (!(hS[S_RR] == hS[S_RR])) { set_error("Krylov iteration produced NaN"); break; }
+        if (hS[S_RR] <= target2) done = true;
+        if (hS[S_BREAK] != 0.0) break;
+    }
+    // true residual
+    if ((rc = s.spmv(x, s.t))) return rc;
+    k_residual0<<<nb, kVecThreads, 0, st>>>(n, d, rhs, s.t);
+    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.t, s.partial);
+    RB_LAUNCH_CHECK("true residual");
+    if ((rc = s.reduce(1))) return rc;
+    double rr = 0.0;
+    int sing = 0;
+    RB_CUDA(cudaMemcpyAsync(&rr, s.red, sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaMemcpyAsync(&sing, s.singular, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    info->iterations = it;
+    info->rel_residual = sqrt(rr / (bb > 0.0 ? bb : 1.0));
+    info->converged = done ? 1 : 0;
+    if (sing) set_error("block-Jacobi: %d singular diagonal blocks replaced by identity", sing);
+    return 0;
+}

@@ -26,12 +26,14 @@ __global__ void __launch_bounds__(256) spmv_kernel(int n, const int32_t* __restr
     const int lane = threadIdx.x % G;
     const int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
+    // the G lanes of a row leave the loop together; other rows of the warp may leave earlier -> group-local shuffle mask
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     for (int64_t r = row0; r < n; r += stride) {
         const int lo = indptr[r], hi = indptr[r + 1];
         double s = 0.0;
         for (int k = lo + lane; k < hi; k += G) s = fma(data[k], x[indices[k]], s);
 #pragma unroll
-        for (int o = G / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, G);
+        for (int o = G / 2; o; o >>= 1) s += __shfl_xor_sync(gmask, s, o, G);
         if (lane == 0) y[r] = s;
     }
 }

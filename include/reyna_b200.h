@@ -155,7 +155,9 @@ typedef struct {
 typedef struct {
     int32_t iterations;
     double  rel_residual;      /* true residual ||b - A x|| / ||b|| at exit                                   */
-    int32_t converged;
+    int32_t converged;         /* true residual <= rtol                                                      */
+    int32_t restarts;          /* restarts from the true residual after the recurrence residual converged     */
+    int32_t stagnated;         /* a restart no longer reduced the true residual: rounding floor reached       */
 } rb_solve_info;
 
 typedef int (*rb_halo_fn)(void *user, double *x_dev, void *stream);          /* refresh ghosts of x            */
@@ -172,9 +174,32 @@ int reyna_b200_solve(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d, i
 int reyna_b200_spmv(int32_t n_rows_scalar, int32_t d, int blocked, const int32_t *indptr, const int32_t *indices,
                     const double *data, const double *x, double *y, void *stream);
 
+/* Error norms of a computed solution (replaces DGFEM.errors, main.py:476-615, and error_assembly/full_assembly.py:9-187,
+ * error_assembly/boundary_assembly.py:8-129).  Samples are q-major like rb_coefs; NULL <=> term absent. */
+typedef struct {
+    const double *vol_u;       /* [Qv][n_tri]        exact solution at the volume points                      */
+    const double *vol_gu;      /* [Qv][n_tri][2]     its gradient (required iff vol_a given)                   */
+    const double *vol_a;       /* [Qv][n_tri][2][2]  diffusion                                                 */
+    const double *vol_c0;      /* [Qv][n_tri]        reaction - div(advection)/2  (main.py:517)                */
+    const double *if_a_mid;    /* [n_iface][2][2]    diffusion at interior edge midpoints                      */
+    const double *if_b;        /* [Qe][n_iface][2]   advection at interior face points                         */
+    const double *bf_u;        /* [Qe][n_bface]      exact solution at boundary face points                    */
+    const double *bf_a_mid;    /* [n_bface][2][2]                                                              */
+    const double *bf_b;        /* [Qe][n_bface][2]                                                             */
+    const uint8_t *bf_flags;   /* [n_bface] bit0 = elliptic (boundary_information.py:76-84)                    */
+} rb_err_samples;
+
+size_t reyna_b200_errors_workspace(void);
+/* out3 (device) = { ||u-uh||_L2^2, |||u-uh|||_DG^2, |u-uh|_H1^2 }; the caller takes the square roots (main.py:608-610). */
+int reyna_b200_errors(const rb_geom *g, const rb_quad *q, const rb_err_samples *s, double sigma_D,
+                      const double *solution, double *out3, void *workspace, size_t workspace_bytes, void *stream);
+
 /* FP64 FMA micro-benchmark used as the compute roofline denominator: runs `iters` dependent-chain FMAs on every
  * lane of a full grid and returns the flop count through *flops (host). */
 int reyna_b200_fma_probe(int iters, double *scratch_dev, double *flops, void *stream);
+
+/* Number of CUDA kernels this library has launched in the calling process (monotone; bench.py reports the delta). */
+unsigned long long reyna_b200_launch_count(void);
 
 const char *reyna_b200_last_error(void);
 const char *reyna_b200_version(void);

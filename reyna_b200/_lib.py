@@ -18,8 +18,9 @@ RB_MAX_QE = 4
 EXPORTS = (
     "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_csr_pattern", "reyna_b200_assemble",
     "reyna_b200_boundary", "reyna_b200_compact_workspace", "reyna_b200_compact_count", "reyna_b200_compact_fill",
-    "reyna_b200_solve_workspace", "reyna_b200_solve", "reyna_b200_spmv", "reyna_b200_fma_probe",
-    "reyna_b200_last_error", "reyna_b200_version",
+    "reyna_b200_solve_workspace", "reyna_b200_solve", "reyna_b200_spmv", "reyna_b200_errors_workspace",
+    "reyna_b200_errors", "reyna_b200_fma_probe",
+    "reyna_b200_launch_count", "reyna_b200_last_error", "reyna_b200_version",
 )
 
 
@@ -39,6 +40,11 @@ class RbCoefs(C.Structure):
                                           "bf_a", "bf_b", "bf_g", "bf_a_mid")]
 
 
+class RbErrSamples(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("vol_u", "vol_gu", "vol_a", "vol_c0", "if_a_mid", "if_b", "bf_u", "bf_a_mid",
+                                          "bf_b", "bf_flags")]
+
+
 class RbStructure(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("adj_off", "adj_item", "grp_off", "counts")] + \
                [(n, C.c_int32) for n in ("n_items", "n_groups", "n_dup_items", "max_items")]
@@ -49,7 +55,8 @@ class RbSolveOpts(C.Structure):
 
 
 class RbSolveInfo(C.Structure):
-    _fields_ = [("iterations", C.c_int32), ("rel_residual", C.c_double), ("converged", C.c_int32)]
+    _fields_ = [("iterations", C.c_int32), ("rel_residual", C.c_double), ("converged", C.c_int32),
+                ("restarts", C.c_int32), ("stagnated", C.c_int32)]
 
 
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
@@ -110,8 +117,15 @@ def lib() -> C.CDLL:
                                    C.POINTER(RbSolveInfo), vp, vp, vp, vp, C.c_size_t, vp]
     L.reyna_b200_spmv.restype = C.c_int
     L.reyna_b200_spmv.argtypes = [i32, i32, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.reyna_b200_errors_workspace.restype = C.c_size_t
+    L.reyna_b200_errors_workspace.argtypes = []
+    L.reyna_b200_errors.restype = C.c_int
+    L.reyna_b200_errors.argtypes = [C.POINTER(RbGeom), C.POINTER(RbQuad), C.POINTER(RbErrSamples), C.c_double, vp, vp,
+                                    vp, C.c_size_t, vp]
     L.reyna_b200_fma_probe.restype = C.c_int
     L.reyna_b200_fma_probe.argtypes = [C.c_int, vp, C.POINTER(C.c_double), vp]
+    L.reyna_b200_launch_count.restype = C.c_ulonglong
+    L.reyna_b200_launch_count.argtypes = []
     L.reyna_b200_last_error.restype = C.c_char_p
     L.reyna_b200_version.restype = C.c_char_p
     _lib = L

@@ -9,6 +9,7 @@
 namespace rb {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of the library is counted (reyna_b200_launch_count)
 
 inline int check_cuda(cudaError_t e, const char* what) {
     if (e != cudaSuccess) {
@@ -26,6 +27,7 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 #define RB_LAUNCH_CHECK(name)                             \
     do {                                                  \
+        rb::count_launch();                               \
         int _rc = rb::check_cuda(cudaGetLastError(), name); \
         if (_rc) return _rc;                              \
     } while (0)

@@ -360,6 +360,8 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     info->iterations = 0;
     info->rel_residual = 0.0;
     info->converged = 0;
+    info->restarts = 0;
+    info->stagnated = 0;
     if (n == 0) { info->converged = 1; return 0; }
 
     Solver s;
@@ -392,85 +394,102 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     RB_LAUNCH_CHECK("block_jacobi_setup");
 
     int rc;
-    // r = b - A x   (x carries the initial guess; ghosts refreshed by the callback)
-    if ((rc = s.spmv(x, s.r))) return rc;
-    k_residual0<<<nb, kVecThreads, 0, st>>>(n, d, rhs, s.r);
-    RB_LAUNCH_CHECK("k_residual0");
-
     const bool cg = opts->method == 0;
     const int check = opts->check_every > 0 ? opts->check_every : 25;
     double hS[S_COUNT];
-    if (cg) {
-        k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
-        RB_CUDA(cudaMemcpyAsync(s.p, s.z, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-        k_dots3<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, rhs, s.partial);     // (r,z), (r,r), (b,b)
-    } else {
-        RB_CUDA(cudaMemcpyAsync(s.rhat, s.r, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-        k_dots3<<<nb, kVecThreads, 0, st>>>(n, s.r, s.r, rhs, s.partial);     // (r,r), (r,r), (b,b)
-    }
-    RB_LAUNCH_CHECK("k_dots3");
-    if ((rc = s.reduce(3))) return rc;
-    scal_init<<<1, 1, 0, st>>>(s.S, s.red);
-    RB_CUDA(cudaMemcpyAsync(hS, s.S, sizeof(hS), cudaMemcpyDeviceToHost, st));
-    RB_CUDA(cudaStreamSynchronize(st));
-    const double bb = hS[S_BB];
-    const double target2 = opts->rtol * opts->rtol * (bb > 0.0 ? bb : 1.0);
-    int it = 0;
-    bool done = hS[S_RR] <= target2;
-    while (!done && it < opts->max_iter) {
-        const int burst = (opts->max_iter - it) < check ? (opts->max_iter - it) : check;
-        for (int k = 0; k < burst; ++k) {
-            if (cg) {
-                if ((rc = s.spmv(s.p, s.v))) return rc;                                  // q = A p
-                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.p, s.v, s.partial);               // (p,q)
-                if ((rc = s.reduce(1))) return rc;
-                scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
-                k_cg_xr<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.p, s.r, s.v);
-                k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
-                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, s.partial);               // (r,z), (r,r)
-                if ((rc = s.reduce(2))) return rc;
-                scal_rho_cg<<<1, 1, 0, st>>>(s.S, s.red);
-                k_cg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.z, s.p);
-            } else {
-                k_bicg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v, s.p);
-                k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.p, s.y);
-                if ((rc = s.spmv(s.y, s.v))) return rc;                                  // v = A y
-                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.rhat, s.v, s.partial);            // (rhat, v)
-                if ((rc = s.reduce(1))) return rc;
-                scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
-                k_bicg_s<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v);                   // r := s
-                k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
-                if ((rc = s.spmv(s.z, s.t))) return rc;                                  // t = A z
-                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.r, s.partial);               // (t,s), (t,t)
-                if ((rc = s.reduce(2))) return rc;
-                scal_omega<<<1, 1, 0, st>>>(s.S, s.red);
-                k_bicg_x<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.y, s.z, s.r, s.t, s.rhat, s.partial);
-                if ((rc = s.reduce(2))) return rc;
-                scal_rho_bicg<<<1, 1, 0, st>>>(s.S, s.red);
-            }
+    double bb = 0.0, target2 = 0.0;
+    int it = 0, restarts = 0;
+    bool done = false, stagnated = false;
+    double true_rr = 0.0, prev_true_rr = -1.0;
+
+    // (Re)start from the current x: r = b - A x (true residual), Krylov state reset.  The recurrence residual drifts away
+    // from the true one on ill-conditioned systems, so convergence is only ever declared on a true residual.
+    for (;;) {
+        if ((rc = s.spmv(x, s.r))) return rc;
+        k_residual0<<<nb, kVecThreads, 0, st>>>(n, d, rhs, s.r);
+        RB_LAUNCH_CHECK("k_residual0");
+        if (cg) {
+            k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+            RB_CUDA(cudaMemcpyAsync(s.p, s.z, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            k_dots3<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, rhs, s.partial);     // (r,z), (r,r), (b,b)
+        } else {
+            RB_CUDA(cudaMemcpyAsync(s.rhat, s.r, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            RB_CUDA(cudaMemsetAsync(s.p, 0, sizeof(double) * n, st));
+            RB_CUDA(cudaMemsetAsync(s.v, 0, sizeof(double) * n, st));
+            k_dots3<<<nb, kVecThreads, 0, st>>>(n, s.r, s.r, rhs, s.partial);     // (r,r), (r,r), (b,b)
         }
-        RB_LAUNCH_CHECK("krylov burst");
-        it += burst;
+        RB_LAUNCH_CHECK("k_dots3");
+        if ((rc = s.reduce(3))) return rc;
+        scal_init<<<1, 1, 0, st>>>(s.S, s.red);
         RB_CUDA(cudaMemcpyAsync(hS, s.S, sizeof(hS), cudaMemcpyDeviceToHost, st));
         RB_CUDA(cudaStreamSynchronize(st));
-        if (!(hS[S_RR] == hS[S_RR])) { set_error("Krylov iteration produced NaN"); break; }
-        if (hS[S_RR] <= target2) done = true;
-        if (hS[S_BREAK] != 0.0) break;
+        bb = hS[S_BB];
+        target2 = opts->rtol * opts->rtol * (bb > 0.0 ? bb : 1.0);
+        true_rr = hS[S_RR];
+        if (!(true_rr == true_rr)) { set_error("Krylov iteration produced NaN"); break; }
+        if (true_rr <= target2) { done = true; break; }
+        if (prev_true_rr >= 0.0 && true_rr > 0.25 * prev_true_rr) { stagnated = true; break; }   // rounding floor
+        if (it >= opts->max_iter || restarts > 20) break;
+        if (prev_true_rr >= 0.0) ++restarts;
+        prev_true_rr = true_rr;
+
+        bool inner_done = false, broke = false;
+        double best_rr = true_rr;
+        int stale_checks = 0;
+        while (!inner_done && it < opts->max_iter) {
+            const int burst = (opts->max_iter - it) < check ? (opts->max_iter - it) : check;
+            for (int k = 0; k < burst; ++k) {
+                if (cg) {
+                    if ((rc = s.spmv(s.p, s.v))) return rc;                                  // q = A p
+                    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.p, s.v, s.partial);               // (p,q)
+                    if ((rc = s.reduce(1))) return rc;
+                    scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
+                    k_cg_xr<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.p, s.r, s.v);
+                    k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+                    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, s.partial);               // (r,z), (r,r)
+                    if ((rc = s.reduce(2))) return rc;
+                    scal_rho_cg<<<1, 1, 0, st>>>(s.S, s.red);
+                    k_cg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.z, s.p);
+                } else {
+                    k_bicg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v, s.p);
+                    k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.p, s.y);
+                    if ((rc = s.spmv(s.y, s.v))) return rc;                                  // v = A y
+                    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.rhat, s.v, s.partial);            // (rhat, v)
+                    if ((rc = s.reduce(1))) return rc;
+                    scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
+                    k_bicg_s<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v);                   // r := s
+                    k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+                    if ((rc = s.spmv(s.z, s.t))) return rc;                                  // t = A z
+                    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.r, s.partial);               // (t,s), (t,t)
+                    if ((rc = s.reduce(2))) return rc;
+                    scal_omega<<<1, 1, 0, st>>>(s.S, s.red);
+                    k_bicg_x<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.y, s.z, s.r, s.t, s.rhat, s.partial);
+                    if ((rc = s.reduce(2))) return rc;
+                    scal_rho_bicg<<<1, 1, 0, st>>>(s.S, s.red);
+                }
+            }
+            RB_LAUNCH_CHECK("krylov burst");
+            it += burst;
+            RB_CUDA(cudaMemcpyAsync(hS, s.S, sizeof(hS), cudaMemcpyDeviceToHost, st));
+            RB_CUDA(cudaStreamSynchronize(st));
+            if (!(hS[S_RR] == hS[S_RR])) { set_error("Krylov iteration produced NaN"); broke = true; break; }
+            if (hS[S_RR] <= target2) inner_done = true;
+            if (hS[S_BREAK] != 0.0) { broke = true; break; }
+            // the recurrence residual no longer improves: hand over to the true-residual check at the loop head
+            if (hS[S_RR] < 0.9 * best_rr) { best_rr = hS[S_RR]; stale_checks = 0; }
+            else if (++stale_checks >= 40) break;
+        }
+        (void)broke;   // a breakdown is handled like a restart: the loop head recomputes the true residual
     }
-    // true residual
-    if ((rc = s.spmv(x, s.t))) return rc;
-    k_residual0<<<nb, kVecThreads, 0, st>>>(n, d, rhs, s.t);
-    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.t, s.partial);
-    RB_LAUNCH_CHECK("true residual");
-    if ((rc = s.reduce(1))) return rc;
-    double rr = 0.0;
+    const double rr = true_rr;
     int sing = 0;
-    RB_CUDA(cudaMemcpyAsync(&rr, s.red, sizeof(double), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaMemcpyAsync(&sing, s.singular, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
     info->iterations = it;
     info->rel_residual = sqrt(rr / (bb > 0.0 ? bb : 1.0));
     info->converged = done ? 1 : 0;
+    info->restarts = restarts;
+    info->stagnated = stagnated ? 1 : 0;
     if (sing) set_error("block-Jacobi: %d singular diagonal blocks replaced by identity", sing);
     return 0;
 }

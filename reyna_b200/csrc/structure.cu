@@ -17,6 +17,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 // ----------------------------------------------------------------------------------------------------------------
 // exclusive scan (three launches; integer, deterministic)
 // ----------------------------------------------------------------------------------------------------------------
@@ -403,4 +406,5 @@ extern "C" int reyna_b200_compact_fill(int32_t n, const int32_t* indptr, const i
 }
 
 extern "C" const char* reyna_b200_last_error(void) { return rb::g_err; }
+extern "C" unsigned long long reyna_b200_launch_count(void) { return rb::g_launches; }
 extern "C" const char* reyna_b200_version(void) { return "reyna_b200 0.1 (sm_100a)"; }

@@ -207,6 +207,52 @@ class DGFEMGeometry:
                          if k != ('mesh' if save_mesh else '') and not k.startswith('_')}, file)
 
 
+_CACHE_ARRAYS = ('elem_bounding_boxes', 'boundary_edges', 'boundary_edges_to_element', 'interior_edges',
+                 'interior_edges_to_element', 'boundary_normals', 'interior_normals', 'subtriangulation',
+                 'triangle_to_polygon', 'h_s', 'areas')
+
+
+def save_geometry_cache(geometry: "DGFEMGeometry", path: str) -> None:
+    """Write mesh + geometry as ONE flat ``.npz`` (uncompressed: loading a 1M-element geometry takes about a second).
+
+    This is the cache BASELINE config 5 asks for ("cached, generated once on host"); it replaces the reference's pickle of
+    Python lists (``save_geometry``, geometry/two_dimensional/DGFEM.py:257-269), which has no loader."""
+    off, idx = flatten_regions(geometry.mesh.filtered_regions)
+    out = dict(vertices=np.asarray(geometry.nodes), region_offsets=off, region_indices=idx,
+               filtered_points=np.asarray(geometry.mesh.filtered_points), h=np.float64(geometry.h))
+    dom = getattr(geometry.mesh, 'domain', None)
+    if dom is not None and hasattr(dom, 'bounding_box'):
+        out['domain_box'] = np.asarray(dom.bounding_box, dtype=float)
+    for name in _CACHE_ARRAYS:
+        v = getattr(geometry, name)
+        if v is not None:
+            out[name] = np.asarray(v)
+    tmp = path + '.tmp.npz'
+    np.savez(tmp, **out)
+    import os
+    os.replace(tmp, path)
+
+
+def load_geometry_cache(path: str) -> "DGFEMGeometry":
+    """Rebuild a ``DGFEMGeometry`` from ``save_geometry_cache`` output without recomputing anything."""
+    from .mesh import FlatRegions, PolyMesh, RectangleDomain
+    z = np.load(path)
+    dom = RectangleDomain(z['domain_box']) if 'domain_box' in z.files else None
+    mesh = PolyMesh(z['vertices'], FlatRegions(z['region_offsets'], z['region_indices']), z['filtered_points'], dom)
+    g = DGFEMGeometry.__new__(DGFEMGeometry)
+    g.mesh = mesh
+    g.nodes = mesh.vertices
+    g.n_nodes = mesh.vertices.shape[0]
+    g.n_elements = len(mesh.filtered_regions)
+    for name in _CACHE_ARRAYS:
+        setattr(g, name, z[name] if name in z.files else None)
+    g.n_triangles = g.subtriangulation.shape[0]
+    g.h = float(z['h'])
+    g._subtriangulation_mode = 'cached'
+    g._flat = None
+    return g
+
+
 def flat_geometry(geometry) -> types.SimpleNamespace:
     """Flat int32/float64 host arrays of any object with the reference's DGFEMGeometry attributes (cached on it)."""
     cached = getattr(geometry, '_rb_flat', None)

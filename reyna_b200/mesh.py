@@ -179,3 +179,73 @@ def voronoi_mesh(n_points: int, seed: int = 1337, lloyd_iterations: int = 3, bou
     # snap boundary vertices onto the rectangle (the reflection puts them there up to rounding)
     regions = FlatRegions(off, inv.astype(np.int64))
     return PolyMesh(vertices, regions, np.ascontiguousarray(pts), RectangleDomain(box))
+
+
+def tiled_voronoi_mesh(n_points: int, tiles: int = 4, seed: int = 1337, lloyd_iterations: int = 3,
+                       bounding_box=((0.0, 1.0), (0.0, 1.0))) -> PolyMesh:
+    """Large synthetic Voronoi mesh from ``tiles x tiles`` mirrored copies of one ``n_points / tiles^2``-element mesh.
+
+    A bounded Voronoi mesh of a rectangle IS the restriction of the Voronoi diagram of the seeds plus their mirror images
+    across the sides (that is how ``_cells`` and the reference's ``_poly_mesher_reflect`` bound it), so gluing alternately
+    mirrored copies of a base mesh gives exactly the bounded Voronoi mesh of the tiled seed set: conforming across the
+    tile sides, convex cells, same element statistics -- at 1/tiles^2 of the qhull cost (1M elements in seconds instead
+    of minutes).  Tiles follow a Z-order curve and elements keep the base mesh's Morton order inside a tile, so the global
+    element numbering is spatially local (contiguous index ranges are compact patches: the multi-GPU partition)."""
+    k = int(tiles)
+    if k < 1 or n_points % (k * k):
+        raise ValueError("n_points must be a multiple of tiles^2")
+    box = np.asarray(bounding_box, dtype=float)
+    base = voronoi_mesh(n_points // (k * k), seed=seed, lloyd_iterations=lloyd_iterations,
+                        bounding_box=((0.0, 1.0), (0.0, 1.0)), morton=True)
+    off, idx = flatten_regions(base.filtered_regions)
+    bv, bp = base.vertices, base.filtered_points
+    nv, ne = bv.shape[0], bp.shape[0]
+    cnt = np.diff(off)
+    # reversed vertex order inside each polygon (a single mirror flips the orientation; keep every cell counter-clockwise)
+    pos = np.arange(idx.shape[0], dtype=np.int64) - np.repeat(off[:-1], cnt)
+    rev = np.repeat(off[:-1] + cnt - 1, cnt) - pos
+    idx_rev = idx[rev]
+
+    tx, ty = np.meshgrid(np.arange(k), np.arange(k), indexing='ij')
+    tx, ty = tx.ravel(), ty.ravel()
+    order = morton_order(np.column_stack((tx, ty)).astype(float) + 0.5, bits=8) if k > 1 else np.array([0])
+    V = np.empty((k * k * nv, 2))
+    P = np.empty((k * k * ne, 2))
+    I = np.empty(k * k * idx.shape[0], dtype=np.int64)
+    for slot, t in enumerate(order):
+        i, j = int(tx[t]), int(ty[t])
+        fx, fy = i % 2 == 1, j % 2 == 1
+        vx = (1.0 - bv[:, 0]) if fx else bv[:, 0]
+        vy = (1.0 - bv[:, 1]) if fy else bv[:, 1]
+        V[slot * nv:(slot + 1) * nv, 0] = (i + vx) / k
+        V[slot * nv:(slot + 1) * nv, 1] = (j + vy) / k
+        px = (1.0 - bp[:, 0]) if fx else bp[:, 0]
+        py = (1.0 - bp[:, 1]) if fy else bp[:, 1]
+        P[slot * ne:(slot + 1) * ne, 0] = (i + px) / k
+        P[slot * ne:(slot + 1) * ne, 1] = (j + py) / k
+        I[slot * idx.shape[0]:(slot + 1) * idx.shape[0]] = (idx_rev if (fx != fy) else idx) + slot * nv
+    # merge the duplicated vertices on the shared tile sides: only vertices lying on a side of the base tile can coincide
+    eps = 1e-12
+    on_side = (np.abs(bv[:, 0]) < eps) | (np.abs(bv[:, 0] - 1.0) < eps) | (np.abs(bv[:, 1]) < eps) | \
+              (np.abs(bv[:, 1] - 1.0) < eps)
+    side_ids = (np.flatnonzero(on_side)[None, :] + (np.arange(k * k) * nv)[:, None]).ravel()
+    q = np.rint(V[side_ids] * float(1 << 44)).astype(np.int64)
+    srt = np.lexsort((q[:, 1], q[:, 0]))
+    qs = q[srt]
+    newgrp = np.ones(qs.shape[0], dtype=bool)
+    newgrp[1:] = np.any(qs[1:] != qs[:-1], axis=1)
+    grp = np.cumsum(newgrp) - 1
+    rep = side_ids[srt][np.flatnonzero(newgrp)]            # representative (first) vertex of every group
+    remap = np.arange(V.shape[0], dtype=np.int64)
+    remap[side_ids[srt]] = rep[grp]
+    keep = np.zeros(V.shape[0], dtype=bool)
+    keep[remap] = True
+    newid = np.cumsum(keep) - 1
+    inv = newid[remap]
+    vertices = V[keep]
+    offsets = np.concatenate([off[:-1] + s * idx.shape[0] for s in range(k * k)] + [[k * k * idx.shape[0]]]).astype(np.int64)
+    w, h = box[0, 1] - box[0, 0], box[1, 1] - box[1, 0]
+    vertices = vertices * np.array([w, h]) + box[:, 0]
+    P = P * np.array([w, h]) + box[:, 0]
+    return PolyMesh(np.ascontiguousarray(vertices), FlatRegions(offsets, inv[I].astype(np.int64)),
+                    np.ascontiguousarray(P), RectangleDomain(box))

@@ -1,0 +1,261 @@
+"""Parity of the CUDA path (through DGFEM -> ctypes -> libreyna_b200.so) with the reference.
+
+* golden fixtures (outputs of the unmodified reference, tests/golden/) -- every case;
+* the CPU oracle on larger synthetic meshes (same geometry object handed to both);
+* size-independent properties at benchmark scale (polynomial exactness from the reference's own test-suite,
+  symmetry of the pure-diffusion matrix, B @ 1 identities, determinism, CSR canonical form).
+Tolerances are the north star's: pattern identical (up to rounding-noise entries, see tests/util.compare_csr), entries
+1e-12 block-relative, solution 1e-9 relative L2, errors to 3 significant digits.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from reyna_b200.problems import PROBLEMS
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import reyna_b200
+    reyna_b200.lib()   # raises if the extension is missing: no silent fallback
+    return reyna_b200
+
+
+def _run(rb, geo, name, p, solve=True, **opts):
+    dg = rb.DGFEM(geo, polynomial_degree=p)
+    dg.add_data(**PROBLEMS[name]["data"])
+    dg.solver_options.update(opts)
+    dg.dgfem(solve=solve)
+    return dg
+
+
+@pytest.mark.parametrize("mesh,key", util.golden_cases())
+def test_golden_parity(rb, mesh, key):
+    z, geo = util.load_golden(mesh)
+    name, p = util.split_case(key)
+    Bref, Lref, xref = util.golden_system(z, key)
+    dg = _run(rb, geo, name, p)
+    B = dg.B
+    assert B.indices.dtype == np.int32 and B.indptr.dtype == np.int32
+    assert B.has_canonical_format
+    max_rel, bad, noise = util.compare_csr(B, Bref, dg.dim_elem)
+    assert bad == 0, f"{bad} pattern mismatches that are not rounding noise"
+    assert max_rel <= util.TOL_ENTRY
+    if noise == 0:
+        assert np.array_equal(B.indptr, Bref.indptr) and np.array_equal(B.indices, Bref.indices)
+    L = np.asarray(dg.L.todense()).reshape(-1)
+    assert util.rel_inf(L, Lref) <= util.TOL_ENTRY
+    assert dg.L.shape == (dg.dim_system, 1)
+    assert util.rel_l2(dg.solution, xref) <= util.TOL_SOLUTION, dg.solve_info
+    if key + "_errors" in z.files:
+        pr = PROBLEMS[name]
+        has_diff = pr["data"].get("diffusion") is not None
+        e = dg.errors(exact_solution=pr["exact"], grad_exact_solution=pr["grad_exact"] if has_diff else None)
+        eref = z[key + "_errors"]
+        assert abs(e[0] - eref[0]) <= util.TOL_ERRORS * abs(eref[0])
+        assert abs(e[1] - eref[1]) <= util.TOL_ERRORS * abs(eref[1])
+        if has_diff:
+            assert abs(e[2] - eref[2]) <= util.TOL_ERRORS * abs(eref[2])
+        else:
+            assert e[2] is None
+
+
+@pytest.mark.parametrize("E,name,p", [(3000, "adr", 2), (3000, "variable", 3), (5000, "variable_hyperbolic", 2),
+                                      (5000, "diffusion", 1), (2000, "hyperbolic", 3), (2000, "adr_tensor", 1)])
+def test_oracle_parity_synthetic(rb, E, name, p):
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(E, seed=E + p), subtriangulation="fan")
+    dg = _run(rb, geo, name, p)
+    B, L, info = dg_oracle.assemble(geo, p, **PROBLEMS[name]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
+    x = dg_oracle.solve(B, L)
+    assert util.rel_l2(dg.solution, x) <= util.TOL_SOLUTION, dg.solve_info
+    pr = PROBLEMS[name]
+    if pr["exact"] is not None:
+        has_diff = pr["data"].get("diffusion") is not None
+        e = dg.errors(exact_solution=pr["exact"], grad_exact_solution=pr["grad_exact"] if has_diff else None)
+        eo = dg_oracle.errors(geo, p, x, pr["exact"], pr["grad_exact"] if has_diff else None,
+                              advection=pr["data"].get("advection"), diffusion=pr["data"].get("diffusion"),
+                              reaction=pr["data"].get("reaction"))
+        for a, b in zip(e, eo):
+            if b is not None:
+                assert abs(a - b) <= util.TOL_ERRORS * abs(b)
+
+
+def test_tiled_and_delaunay_subtriangulation(rb):
+    """Mirrored-tile mesh (merged side vertices) with the reference's per-polygon Delaunay sub-triangulation."""
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(1024, tiles=2, seed=5))
+    dg = _run(rb, geo, "variable", 2)
+    B, L, info = dg_oracle.assemble(geo, 2, **PROBLEMS["variable"]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_l2(dg.solution, dg_oracle.solve(B, L)) <= util.TOL_SOLUTION
+
+
+# ---- the reference's polynomial-exactness known-answer tests (tests/test_DGFEM.py:85-479), at benchmark-like size --------
+def _identity(x):
+    out = np.zeros((x.shape[0], 2, 2), dtype=np.float64)
+    for i in range(x.shape[0]):
+        out[i, 0, 0] = 1.0
+        out[i, 1, 1] = 1.0
+    return out
+
+
+def _nondiag(x):
+    out = np.zeros((x.shape[0], 2, 2), dtype=np.float64)
+    for i in range(x.shape[0]):
+        out[i, 0, 0] = 2.0
+        out[i, 0, 1] = 1.0
+        out[i, 1, 0] = 1.0
+        out[i, 1, 1] = 3.0
+    return out
+
+
+def test_exactness_advection_linear_p1(rb):
+    # tests/test_DGFEM.py:109-133: b = (1,1), u = x + y, f = 2
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(20000, seed=1), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=1)
+    dg.add_data(advection=lambda x: np.ones(x.shape, dtype=np.float64),
+                forcing=lambda x: 2.0 * np.ones(x.shape[0], dtype=np.float64),
+                dirichlet_bcs=lambda x: x[:, 0] + x[:, 1])
+    dg.dgfem(solve=True)
+    l2, dgn, h1 = dg.errors(exact_solution=lambda x: x[:, 0] + x[:, 1])
+    assert h1 is None and l2 < 1e-10 and dgn < 1e-10
+
+
+def test_exactness_advection_reaction_quadratic_p2(rb):
+    # tests/test_DGFEM.py:215-243: b = (1,1), c = 1, u = x^2 + y^2
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(20000, seed=2), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=2)
+    dg.add_data(advection=lambda x: np.ones(x.shape, dtype=np.float64),
+                reaction=lambda x: np.ones(x.shape[0], dtype=np.float64),
+                forcing=lambda x: 2.0 * x[:, 0] + 2.0 * x[:, 1] + x[:, 0] ** 2 + x[:, 1] ** 2,
+                dirichlet_bcs=lambda x: x[:, 0] ** 2 + x[:, 1] ** 2)
+    dg.dgfem(solve=True)
+    l2, dgn, _ = dg.errors(exact_solution=lambda x: x[:, 0] ** 2 + x[:, 1] ** 2)
+    assert l2 < 1e-10 and dgn < 1e-10
+
+
+def test_exactness_diffusion_quadratic_p2(rb):
+    # tests/test_DGFEM.py:335-367: a = I, u = x^2 + y^2, f = -4
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(4000, seed=3), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=2)
+    dg.add_data(diffusion=_identity, forcing=lambda x: -4.0 * np.ones(x.shape[0], dtype=np.float64),
+                dirichlet_bcs=lambda x: x[:, 0] ** 2 + x[:, 1] ** 2)
+    dg.dgfem(solve=True)
+    l2, dgn, h1 = dg.errors(exact_solution=lambda x: x[:, 0] ** 2 + x[:, 1] ** 2,
+                            grad_exact_solution=lambda x: 2.0 * x)
+    assert l2 < 1e-10 and dgn < 1e-8 and h1 < 1e-8, (l2, dgn, h1, dg.solve_info)
+
+
+def test_exactness_nondiagonal_tensor_p2(rb):
+    # tests/test_DGFEM.py:405-479 (full non-diagonal tensor): a = [[2,1],[1,3]], u = x^2 + x y, -div(a grad u) = -(4 + 2) = -6
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(4000, seed=4), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=2)
+    u = lambda x: x[:, 0] ** 2 + x[:, 0] * x[:, 1]                                          # noqa: E731
+    gu = lambda x: np.vstack((2.0 * x[:, 0] + x[:, 1], x[:, 0])).T                           # noqa: E731
+    dg.add_data(diffusion=_nondiag, forcing=lambda x: -6.0 * np.ones(x.shape[0], dtype=np.float64), dirichlet_bcs=u)
+    dg.dgfem(solve=True)
+    l2, dgn, h1 = dg.errors(exact_solution=u, grad_exact_solution=gu)
+    assert l2 < 1e-10 and dgn < 1e-8 and h1 < 1e-8, (l2, dgn, h1, dg.solve_info)
+
+
+# ---- structural properties at scale -----------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def big(rb):
+    return rb.DGFEMGeometry(rb.tiled_voronoi_mesh(65536, tiles=4, seed=1337), subtriangulation="fan")
+
+
+def test_scale_diffusion_symmetric_and_full_pattern(rb, big):
+    dg = _run(rb, big, "diffusion", 2, solve=False)
+    B = dg.B
+    d, E, F = dg.dim_elem, big.n_elements, big.interior_edges.shape[0]
+    assert B.nnz == d * d * (E + 2 * F)            # full pattern whenever diffusion is present
+    assert B.has_canonical_format and B.indices.dtype == np.int32
+    A = (B - B.T).tocoo()
+    assert np.abs(A.data).max() <= 1e-12 * np.abs(B.data).max()       # SIPG with symmetric a is symmetric
+    # constants are in the kernel of the volume + interior-face diffusion form: (B @ 1)_(e,j) only sees Dirichlet faces
+    one = np.zeros(dg.dim_system)
+    hx = 0.5 * (big.elem_bounding_boxes[:, 1] - big.elem_bounding_boxes[:, 0])
+    hy = 0.5 * (big.elem_bounding_boxes[:, 3] - big.elem_bounding_boxes[:, 2])
+    one[0::d] = 2.0 * np.sqrt(hx * hy)             # coefficient of phi_0 = 1/(2 sqrt(hx hy)) representing u = 1
+    r = (B @ one).reshape(E, d)
+    interior = np.ones(E, dtype=bool)
+    interior[big.boundary_edges_to_element] = False
+    assert np.abs(r[interior]).max() <= 1e-9 * np.abs(B.data).max()
+
+
+def test_scale_hyperbolic_one_sided_pattern(rb, big):
+    dg = _run(rb, big, "hyperbolic", 2, solve=False)
+    d, E, F = dg.dim_elem, big.n_elements, big.interior_edges.shape[0]
+    # advection-only: one off-diagonal block per face, minus rounding-noise zeros
+    assert abs(dg.B.nnz - d * d * (E + F)) <= 1e-3 * d * d * (E + F)
+    assert dg.B.has_canonical_format
+    assert dg.timings["exact_zeros"] >= 0
+
+
+def test_scale_deterministic(rb, big):
+    a = _run(rb, big, "adr", 2, solve=False)
+    b = _run(rb, big, "adr", 2, solve=False)
+    assert np.array_equal(a.B.indptr, b.B.indptr) and np.array_equal(a.B.indices, b.B.indices)
+    assert np.array_equal(a.B.data, b.B.data)                          # bitwise: no floating-point atomics anywhere
+    assert np.array_equal(np.asarray(a.L.todense()), np.asarray(b.L.todense()))
+
+
+def test_scale_oracle_parity_65k_p2(rb, big):
+    """BASELINE config 3a (65k elements, p=2 ADR) entry by entry against the oracle."""
+    from oracle import dg_oracle
+    dg = _run(rb, big, "adr", 2, solve=False)
+    B, L, info = dg_oracle.assemble(big, 2, **PROBLEMS["adr"]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
+
+
+def test_spmv_matches_scipy(rb, big):
+    import ctypes as C
+    import torch
+    dg = _run(rb, big, "adr", 1, solve=False)
+    dv = dg._dev
+    x = torch.linspace(-1.0, 1.0, dv["n"], dtype=torch.float64, device=dv["data"].device)
+    y = torch.empty_like(x)
+    rc = rb.lib().reyna_b200_spmv(dv["n"], dv["d"], int(dv["blocked"]), dv["indptr"].data_ptr(), dv["indices"].data_ptr(),
+                                  dv["data"].data_ptr(), x.data_ptr(), y.data_ptr(),
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    yref = dg.B @ x.cpu().numpy()
+    assert util.rel_inf(y.cpu().numpy(), yref) <= 1e-13
+
+
+def test_geometry_cache_roundtrip_on_device(rb, tmp_path):
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(500, seed=9), subtriangulation="fan")
+    path = str(tmp_path / "g.npz")
+    rb.save_geometry_cache(geo, path)
+    geo2 = rb.load_geometry_cache(path)
+    a = _run(rb, geo, "adr", 2, solve=False)
+    b = _run(rb, geo2, "adr", 2, solve=False)
+    assert np.array_equal(a.B.data, b.B.data) and np.array_equal(a.B.indices, b.B.indices)
+
+
+def test_reference_api_errors_on_gpu(rb):
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(64, seed=1))
+    dg = rb.DGFEM(geo, polynomial_degree=1)
+    dg.add_data(advection=lambda x: np.ones(x.shape, dtype=np.float64),
+                dirichlet_bcs=lambda x: np.ones(x.shape[0], dtype=np.float64))
+    with pytest.raises(AssertionError):
+        dg.dgfem(solve=True, verbose=2)                 # tests/test_DGFEM.py:64-83
+    with pytest.raises(ValueError):
+        dg.errors(exact_solution=lambda x: np.ones(x.shape[0]))      # no solution yet
+    dg.dgfem(solve=True)
+    with pytest.raises(ValueError):                     # tests/test_DGFEM.py:245-268 (mirror: grad without diffusion)
+        dg.errors(exact_solution=lambda x: np.ones(x.shape[0]), grad_exact_solution=lambda x: np.zeros(x.shape))
+    l2, dgn, h1 = dg.errors(exact_solution=lambda x: np.ones(x.shape[0]))
+    assert l2 < 1e-10 and dgn < 1e-10 and h1 is None    # tests/test_DGFEM.py:85-107 constant solution

@@ -117,9 +117,12 @@ int reyna_b200_csr_pattern(const rb_geom *g, const rb_structure *s, int p, int32
 /* Volume + interior-face terms, summed per element in a fixed order and written straight into the CSR value array
  * (replaces DGFEM._stiffness_matrix + localstiff, main.py:275-327 / full_assembly.py:9-77, and
  * DGFEM._interior_stiffness_matrix + int_localstiff, main.py:329-374 / full_assembly.py:80-214).
- * data [nnz], load [n_rows*d]; *zero_count (device int64, caller-zeroed) receives the number of exact zeros written. */
+ * data [nnz], load [n_rows*d]; *zero_count (device int64, caller-zeroed) receives the number of exact zeros written.
+ * workspace: reyna_b200_assemble_workspace() bytes of device scratch (per-element basis scalings, per-face penalties). */
+size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface);
 int reyna_b200_assemble(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
-                        double sigma_D, double *data, double *load, long long *zero_count, void *stream);
+                        double sigma_D, double *data, double *load, long long *zero_count, void *workspace,
+                        size_t workspace_bytes, void *stream);
 
 /* Boundary faces: elliptic (Dirichlet SIPG) and inflow terms subtracted in place from the diagonal blocks and the
  * load (replaces _diffusion_bcs_contribution / _advection_bcs_contribution, main.py:376-474, and

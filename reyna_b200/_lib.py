@@ -9,14 +9,15 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libreyna_b200.so")
+LIB_PATH = os.environ.get("REYNA_B200_LIB") or os.path.join(_HERE, "libreyna_b200.so")   # override: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 
 RB_MAX_QV = 16
 RB_MAX_QE = 4
 
 EXPORTS = (
-    "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_csr_pattern", "reyna_b200_assemble",
+    "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_csr_pattern",
+    "reyna_b200_assemble_workspace", "reyna_b200_assemble",
     "reyna_b200_boundary", "reyna_b200_compact_workspace", "reyna_b200_compact_count", "reyna_b200_compact_fill",
     "reyna_b200_solve_workspace", "reyna_b200_solve", "reyna_b200_spmv", "reyna_b200_errors_workspace",
     "reyna_b200_errors", "reyna_b200_fma_probe",
@@ -100,7 +101,9 @@ def lib() -> C.CDLL:
     L.reyna_b200_csr_pattern.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.c_int, vp, vp, vp]
     L.reyna_b200_assemble.restype = C.c_int
     L.reyna_b200_assemble.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.POINTER(RbCoefs), C.POINTER(RbQuad),
-                                      C.c_double, vp, vp, i64p, vp]
+                                      C.c_double, vp, vp, i64p, vp, C.c_size_t, vp]
+    L.reyna_b200_assemble_workspace.restype = C.c_size_t
+    L.reyna_b200_assemble_workspace.argtypes = [i32, i32]
     L.reyna_b200_boundary.restype = C.c_int
     L.reyna_b200_boundary.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.POINTER(RbCoefs), C.POINTER(RbQuad),
                                       C.c_double, i32, vp, vp, vp, vp, vp, vp, vp, i64p, vp]

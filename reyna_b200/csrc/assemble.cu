@@ -24,6 +24,10 @@
 namespace rb {
 
 constexpr int kBD = 128;   // threads per CTA
+#ifndef RB_FUSE_LIMIT
+#define RB_FUSE_LIMIT 36
+#endif
+constexpr int kFuseLimit = RB_FUSE_LIMIT;   // accumulators per block up to which a face item forms both blocks in one sweep
 
 struct AsmArgs {
     rb_geom g;
@@ -41,7 +45,50 @@ struct AsmArgs {
     unsigned long long* zero_count;
     int te;            // elements per CTA
     int has_dups;      // adjacency contains merged (duplicate-neighbour) items
+    const ElemBox* ebox;   // [n_elem]  bounding-box scalings, written by dg_prepare_kernel
+    const double* fsigma;  // [n_iface] SIPG penalty per interior face (diffusion only), written by dg_prepare_kernel
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// prepass: per-element basis scalings and per-face penalty.  Both are needed by every (element, face) item from either
+// side of a face (and the polygon loops of the penalty are latency-bound), so they are computed once here.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double max_sub_area_g(const rb_geom& g, int e, double2 P0, double ex, double ey) {
+    // |k_b|_K = max over the vertices v of K of 0.5*|(P1-P0) x (v-P0)|   (full_assembly.py:142-143)
+    double kb = 0.0;
+    const int lo = g.poly_off[e], hi = g.poly_off[e + 1];
+    for (int k = lo; k < hi; ++k) {
+        const double2 v = reinterpret_cast<const double2*>(g.nodes)[g.poly_vtx[k]];
+        kb = fmax(kb, 0.5 * fabs(ex * (v.y - P0.y) - ey * (v.x - P0.x)));
+    }
+    return kb;
+}
+
+__global__ void __launch_bounds__(256) dg_prepare_kernel(rb_geom g, const double* __restrict__ if_a_mid, double sigma_pp,
+                                                         double p2, ElemBox* __restrict__ ebox,
+                                                         double* __restrict__ fsigma) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.n_elem; e += stride) ebox[e] = make_box(g.bbox, e);
+    if (if_a_mid == nullptr) return;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.n_iface; f += stride) {
+        const int e1 = g.ielem[2 * (size_t)f], e2 = g.ielem[2 * (size_t)f + 1];
+        const double2 P0 = reinterpret_cast<const double2*>(g.nodes)[g.iedge[2 * (size_t)f]];
+        const double2 P1 = reinterpret_cast<const double2*>(g.nodes)[g.iedge[2 * (size_t)f + 1]];
+        const double2 n = reinterpret_cast<const double2*>(g.inorm)[f];
+        const double2 m0 = reinterpret_cast<const double2*>(if_a_mid)[2 * (size_t)f];
+        const double2 m1 = reinterpret_cast<const double2*>(if_a_mid)[2 * (size_t)f + 1];
+        // lambda = n . a(mid) . n   (full_assembly.py:140)
+        const double lam = (n.x * m0.x + n.y * m1.x) * n.x + (n.x * m0.y + n.y * m1.y) * n.y;
+        const double ex = P1.x - P0.x, ey = P1.y - P0.y;
+        const double tx = 0.5 * ex, ty = 0.5 * ey;
+        const double De = sqrt(tx * tx + ty * ty);
+        const double a1 = g.area[e1], a2 = g.area[e2];
+        const double c1 = fmin(a1 / max_sub_area_g(g, e1, P0, ex, ey), p2);
+        const double c2 = fmin(a2 / max_sub_area_g(g, e2, P0, ex, ey), p2);
+        fsigma[f] = sigma_pp * lam * (2.0 * De) * fmax(c1 / a1, c2 / a2);   // full_assembly.py:146-148
+    }
+}
+
 
 template <int P, int RS>
 struct Dims {
@@ -109,13 +156,38 @@ __device__ __forceinline__ void staged_sum(const double (&vals)[NT], bool active
 // ---------------------------------------------------------------------------------------------------------------
 // phase A: one sub-triangle
 // ---------------------------------------------------------------------------------------------------------------
+struct VolCoef {
+    double a00, a01, a10, a11, b0, b1, c, f;
+};
+
+template <bool DIFF, bool ADV>
+__device__ __forceinline__ VolCoef load_vol_coef(const AsmArgs& A, size_t m) {
+    VolCoef k;
+    k.a00 = k.a01 = k.a10 = k.a11 = k.b0 = k.b1 = 0.0;
+    if (DIFF) {
+        const double2 ar0 = __ldg(reinterpret_cast<const double2*>(A.c.vol_a) + 2 * m);
+        const double2 ar1 = __ldg(reinterpret_cast<const double2*>(A.c.vol_a) + 2 * m + 1);
+        k.a00 = ar0.x; k.a01 = ar0.y; k.a10 = ar1.x; k.a11 = ar1.y;
+    }
+    if (ADV) {
+        const double2 bb = __ldg(reinterpret_cast<const double2*>(A.c.vol_b) + m);
+        k.b0 = bb.x; k.b1 = bb.y;
+    }
+    k.c = A.c.vol_c ? __ldg(A.c.vol_c + m) : 0.0;
+    k.f = A.c.vol_f ? __ldg(A.c.vol_f + m) : 0.0;
+    return k;
+}
+
 template <int P, int RS, int PART, bool DIFF, bool ADV>
 __device__ __forceinline__ void triangle_block(const AsmArgs& A, int t, double (&acc)[Dims<P, RS>::RJ * Dims<P, RS>::D + Dims<P, RS>::RJ]) {
     using DM = Dims<P, RS>;
     constexpr int D = DM::D, RJ = DM::RJ, J0 = PART * RJ;
+    const size_t T = (size_t)A.g.n_tri;
+    // the samples of the first point are requested before the geometry chain (tri -> nodes, tri_elem -> box) resolves
+    VolCoef cur = load_vol_coef<DIFF, ADV>(A, (size_t)t);
     const int e = A.g.tri_elem[t];
-    const ElemBox bx = make_box(A.g.bbox, e);
     const int i0 = A.g.tri[3 * (size_t)t], i1 = A.g.tri[3 * (size_t)t + 1], i2 = A.g.tri[3 * (size_t)t + 2];
+    const ElemBox bx = A.ebox[e];
     const double2 V0 = reinterpret_cast<const double2*>(A.g.nodes)[i0];
     const double2 V1 = reinterpret_cast<const double2*>(A.g.nodes)[i1];
     const double2 V2 = reinterpret_cast<const double2*>(A.g.nodes)[i2];
@@ -123,9 +195,12 @@ __device__ __forceinline__ void triangle_block(const AsmArgs& A, int t, double (
     const double e1x = 0.5 * (V1.x - V0.x), e1y = 0.5 * (V1.y - V0.y);
     const double e2x = 0.5 * (V2.x - V0.x), e2y = 0.5 * (V2.y - V0.y);
     const double hdet = 0.5 * fabs(e1x * e2y - e1y * e2x);
-    const size_t T = (size_t)A.g.n_tri;
 #pragma unroll 1
     for (int q = 0; q < DM::QV; ++q) {
+        // software pipeline: the samples of point q+1 are in flight while point q is contracted (the kernel runs at
+        // 8 warps per SM, so memory latency has to be hidden inside the thread)
+        const int qn = q + 1 < DM::QV ? q + 1 : q;
+        const VolCoef nxt = load_vol_coef<DIFF, ADV>(A, (size_t)qn * T + t);
         const double r0 = A.rvx[q], r1 = A.rvy[q];
         const double l0 = 1.0 - r0 - r1;
         const double x = l0 * V0.x + r0 * V1.x + r1 * V2.x;
@@ -133,30 +208,20 @@ __device__ __forceinline__ void triangle_block(const AsmArgs& A, int t, double (
         double phi[D], gx[D], gy[D];
         eval_basis<P, true>(x, y, bx, A.lc, phi, gx, gy);
         const double W = hdet * A.wv[q];
-        const size_t m = (size_t)q * T + t;
-        double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
-        if (DIFF) {
-            const double2 ar0 = reinterpret_cast<const double2*>(A.c.vol_a)[2 * m];
-            const double2 ar1 = reinterpret_cast<const double2*>(A.c.vol_a)[2 * m + 1];
-            a00 = ar0.x; a01 = ar0.y; a10 = ar1.x; a11 = ar1.y;
-        }
-        if (ADV) {
-            const double2 bb = reinterpret_cast<const double2*>(A.c.vol_b)[m];
-            b0 = bb.x; b1 = bb.y;
-        }
-        const double cq = A.c.vol_c ? A.c.vol_c[m] : 0.0;
+        // W folded into the coefficients once per point
+        const double a00 = W * cur.a00, a01 = W * cur.a01, a10 = W * cur.a10, a11 = W * cur.a11;
+        const double b0 = W * cur.b0, b1 = W * cur.b1, cq = W * cur.c;
         // column (trial i) quantities u = W * grad(phi_i)^T a, s = W * (b.grad(phi_i) + c phi_i) are formed one column
         // at a time so that only the accumulators and the basis stay live
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             double u0 = 0, u1 = 0;
             if (DIFF) {
-                u0 = W * (gx[i] * a00 + gy[i] * a10);
-                u1 = W * (gx[i] * a01 + gy[i] * a11);
+                u0 = fma(gx[i], a00, gy[i] * a10);
+                u1 = fma(gx[i], a01, gy[i] * a11);
             }
             double si = cq * phi[i];
-            if (ADV) si += b0 * gx[i] + b1 * gy[i];
-            si *= W;
+            if (ADV) si = fma(b0, gx[i], fma(b1, gy[i], si));
 #pragma unroll
             for (int jj = 0; jj < RJ; ++jj) {
                 double v = acc[jj * D + i];
@@ -169,10 +234,11 @@ __device__ __forceinline__ void triangle_block(const AsmArgs& A, int t, double (
             }
         }
         if (A.c.vol_f) {
-            const double wf = W * A.c.vol_f[m];
+            const double wf = W * cur.f;
 #pragma unroll
             for (int jj = 0; jj < RJ; ++jj) acc[RJ * D + jj] = fma(wf, phi[J0 + jj], acc[RJ * D + jj]);
         }
+        cur = nxt;
     }
 }
 
@@ -186,19 +252,8 @@ struct FaceCtx {
     bool down;       // this side is the downwind side of the face
 };
 
-__device__ __forceinline__ double max_sub_area(const AsmArgs& A, int e, double2 P0, double ex, double ey) {
-    // |k_b|_K = max over the vertices v of K of 0.5*|(P1-P0) x (v-P0)|   (full_assembly.py:142-143)
-    double kb = 0.0;
-    const int lo = A.g.poly_off[e], hi = A.g.poly_off[e + 1];
-    for (int k = lo; k < hi; ++k) {
-        const double2 v = reinterpret_cast<const double2*>(A.g.nodes)[A.g.poly_vtx[k]];
-        kb = fmax(kb, 0.5 * fabs(ex * (v.y - P0.y) - ey * (v.x - P0.x)));
-    }
-    return kb;
-}
-
 template <bool DIFF>
-__device__ __forceinline__ FaceCtx face_setup(const AsmArgs& A, int e, int item) {
+__device__ __forceinline__ FaceCtx face_setup(const AsmArgs& A, int item) {
     FaceCtx c;
     c.f = item >> 1;
     const int side = item & 1;
@@ -212,19 +267,28 @@ __device__ __forceinline__ FaceCtx face_setup(const AsmArgs& A, int e, int item)
     c.De = sqrt(c.tan.x * c.tan.x + c.tan.y * c.tan.y);
     c.n = reinterpret_cast<const double2*>(A.g.inorm)[c.f];
     c.down = A.c.if_upwind ? ((A.c.if_upwind[c.f] != 0) == (side == 1)) : false;
-    c.sigma = 0.0;
-    if (DIFF) {
-        const double2 m0 = reinterpret_cast<const double2*>(A.c.if_a_mid)[2 * (size_t)c.f];
-        const double2 m1 = reinterpret_cast<const double2*>(A.c.if_a_mid)[2 * (size_t)c.f + 1];
-        // lambda = n . a(mid) . n   (full_assembly.py:140)
-        const double lam = (c.n.x * m0.x + c.n.y * m1.x) * c.n.x + (c.n.x * m0.y + c.n.y * m1.y) * c.n.y;
-        const double ex = P1.x - P0.x, ey = P1.y - P0.y;
-        const double ae = A.g.area[e], ao = A.g.area[c.o];
-        const double ce = fmin(ae / max_sub_area(A, e, P0, ex, ey), A.p2);
-        const double co = fmin(ao / max_sub_area(A, c.o, P0, ex, ey), A.p2);
-        c.sigma = A.sigma_pp * lam * (2.0 * c.De) * fmax(ce / ae, co / ao);   // full_assembly.py:146-148
-    }
+    c.sigma = DIFF ? A.fsigma[c.f] : 0.0;
     return c;
+}
+
+struct FaceCoef {
+    double a00, a01, a10, a11, b0, b1;
+};
+
+template <bool DIFF, bool ADV>
+__device__ __forceinline__ FaceCoef load_face_coef(const AsmArgs& A, size_t m) {
+    FaceCoef k;
+    k.a00 = k.a01 = k.a10 = k.a11 = k.b0 = k.b1 = 0.0;
+    if (DIFF) {
+        const double2 ar0 = __ldg(reinterpret_cast<const double2*>(A.c.if_a) + 2 * m);
+        const double2 ar1 = __ldg(reinterpret_cast<const double2*>(A.c.if_a) + 2 * m + 1);
+        k.a00 = ar0.x; k.a01 = ar0.y; k.a10 = ar1.x; k.a11 = ar1.y;
+    }
+    if (ADV) {
+        const double2 bb = __ldg(reinterpret_cast<const double2*>(A.c.if_b) + m);
+        k.b0 = bb.x; k.b1 = bb.y;
+    }
+    return k;
 }
 
 // Accumulate, for rows [J0, J0+RJ) of element e, the own-element (diagonal) block into dacc and/or the other-element
@@ -236,25 +300,26 @@ __device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, 
     using DM = Dims<P, RS>;
     constexpr int D = DM::D, RJ = DM::RJ, J0 = PART * RJ;
     const size_t F = (size_t)A.g.n_iface;
+    FaceCoef cur = load_face_coef<DIFF, ADV>(A, (size_t)c.f);
 #pragma unroll 1
     for (int q = 0; q < DM::QE; ++q) {
+        const int qn = q + 1 < DM::QE ? q + 1 : q;
+        const FaceCoef nxt = load_face_coef<DIFF, ADV>(A, (size_t)qn * F + c.f);
         const double x = c.mid.x + A.xe[q] * c.tan.x;
         const double y = c.mid.y + A.xe[q] * c.tan.y;
         const double W = c.De * A.we[q];
-        const size_t m = (size_t)q * F + c.f;
         double atn0 = 0, atn1 = 0, gamma = 0;
         if (DIFF) {
-            const double2 ar0 = reinterpret_cast<const double2*>(A.c.if_a)[2 * m];
-            const double2 ar1 = reinterpret_cast<const double2*>(A.c.if_a)[2 * m + 1];
             // F_k = n . (a grad phi_k) = (a^T n) . grad phi_k
-            atn0 = c.n.x * ar0.x + c.n.y * ar1.x;
-            atn1 = c.n.x * ar0.y + c.n.y * ar1.y;
+            atn0 = c.n.x * cur.a00 + c.n.y * cur.a10;
+            atn1 = c.n.x * cur.a01 + c.n.y * cur.a11;
         }
         if (ADV) {
-            const double2 bb = reinterpret_cast<const double2*>(A.c.if_b)[m];
-            const double beta = bb.x * c.n.x + bb.y * c.n.y;
+            const double beta = cur.b0 * c.n.x + cur.b1 * c.n.y;
             gamma = c.down ? -c.sgn * beta : 0.0;
         }
+        const double hw0 = -0.5 * W * atn0, hw1 = -0.5 * W * atn1;     // -W/2 * a^T n
+        const double sg = c.sigma + gamma;
         double phi[D], gx[D], gy[D];
         eval_basis<P, DIFF>(x, y, bxe, A.lc, phi, gx, gy);
         double Pr[RJ], Qr[RJ];
@@ -268,8 +333,8 @@ __device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, 
 #pragma unroll
             for (int i = 0; i < D; ++i) {
                 const double Vc = Ws * phi[i];
-                double Uc = gamma * Vc;
-                if (DIFF) Uc += c.sigma * Vc - (0.5 * W) * (atn0 * gx[i] + atn1 * gy[i]);
+                double Uc = sg * Vc;
+                if (DIFF) Uc = fma(hw0, gx[i], fma(hw1, gy[i], Uc));
 #pragma unroll
                 for (int jj = 0; jj < RJ; ++jj) {
                     double v = dacc[jj * D + i];
@@ -284,8 +349,8 @@ __device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, 
 #pragma unroll
             for (int i = 0; i < D; ++i) {
                 const double Vc = -Ws * phi[i];
-                double Uc = gamma * Vc;
-                if (DIFF) Uc += c.sigma * Vc - (0.5 * W) * (atn0 * gx[i] + atn1 * gy[i]);
+                double Uc = sg * Vc;
+                if (DIFF) Uc = fma(hw0, gx[i], fma(hw1, gy[i], Uc));
 #pragma unroll
                 for (int jj = 0; jj < RJ; ++jj) {
                     double v = oacc[jj * D + i];
@@ -295,6 +360,7 @@ __device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, 
                 }
             }
         }
+        cur = nxt;
     }
 }
 
@@ -304,8 +370,8 @@ __device__ __forceinline__ void item_pass(const AsmArgs& A, int e, int k, int k_
                                           unsigned& zeros) {
     using DM = Dims<P, RS>;
     constexpr int D = DM::D, RJ = DM::RJ, J0 = PART * RJ;
-    constexpr bool FUSE = (RJ * D <= 18);        // both blocks in one sweep when the accumulators are few
-    const ElemBox bxe = make_box(A.g.bbox, e);
+    constexpr bool FUSE = (RJ * D <= kFuseLimit);   // both blocks in one sweep when the accumulators fit in registers
+    const ElemBox bxe = A.ebox[e];
     double oacc[RJ * D];
 #pragma unroll
     for (int v = 0; v < RJ * D; ++v) oacc[v] = 0.0;
@@ -313,8 +379,8 @@ __device__ __forceinline__ void item_pass(const AsmArgs& A, int e, int k, int k_
     int kk = k;
     do {
         const int item = A.adj_item[kk] & 0x7fffffff;
-        const FaceCtx c = face_setup<DIFF>(A, e, item);
-        const ElemBox bxo = make_box(A.g.bbox, c.o);
+        const FaceCtx c = face_setup<DIFF>(A, item);
+        const ElemBox bxo = A.ebox[c.o];
         if (FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, true>(A, c, bxe, bxo, dacc, oacc);
         else face_blocks<P, RS, PART, DIFF, ADV, false, true>(A, c, bxe, bxo, dacc, oacc);
         ++kk;
@@ -343,7 +409,7 @@ __device__ __forceinline__ void item_pass(const AsmArgs& A, int e, int k, int k_
         kk = k;
         do {
             const int item = A.adj_item[kk] & 0x7fffffff;
-            const FaceCtx c = face_setup<DIFF>(A, e, item);
+            const FaceCtx c = face_setup<DIFF>(A, item);
             face_blocks<P, RS, PART, DIFF, ADV, true, false>(A, c, bxe, bxe, dacc, dacc);
             ++kk;
         } while (A.has_dups && kk < k_end && A.adj_item[kk] < 0);
@@ -476,9 +542,32 @@ static int dispatch_coefs(const AsmArgs& A, bool diff, bool adv, cudaStream_t st
 
 using namespace rb;
 
+// elements per CTA: the choice that keeps most lanes busy in both phases (a pass handles kBD/RS items; the last pass of a
+// phase is partially filled)
+static int choose_te(double tris_per_elem, double items_per_elem, int rs, double w_vol, double w_face) {
+    const int it = kBD / rs;
+    int best = 1;
+    double best_u = -1.0;
+    for (int te = 4; te <= 64; ++te) {
+        const double na = te * tris_per_elem, nb = te * items_per_elem;
+        const double ua = na > 0 ? na / (ceil(na / it) * it) : 1.0;
+        const double ub = nb > 0 ? nb / (ceil(nb / it) * it) : 1.0;
+        const double u = (w_vol * ua + w_face * ub) / (w_vol + w_face) - 0.002 * te / 64.0;   // ties -> smaller CTAs
+        if (u > best_u) { best_u = u; best = te; }
+    }
+    return best;
+}
+
+extern "C" size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface) {
+    return sizeof(ElemBox) * (size_t)(n_elem > 0 ? n_elem : 1) + sizeof(double) * (size_t)(n_iface > 0 ? n_iface : 1) + 256;
+}
+
 extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
-                                   double sigma_D, double* data, double* load, long long* zero_count, void* stream) {
-    RB_REQUIRE(g && s && c && q && data && load && zero_count, RB_E_ARG, "reyna_b200_assemble: null argument");
+                                   double sigma_D, double* data, double* load, long long* zero_count, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    RB_REQUIRE(g && s && c && q && data && load && zero_count && workspace, RB_E_ARG, "reyna_b200_assemble: null argument");
+    RB_REQUIRE(workspace_bytes >= reyna_b200_assemble_workspace(g->n_elem, g->n_iface), RB_E_WORKSPACE,
+               "reyna_b200_assemble: workspace too small");
     const int p = q->p;
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_assemble: polynomial degree must be 1..3");
     const bool diff = c->vol_a != nullptr, adv = c->vol_b != nullptr;
@@ -488,6 +577,7 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
     RB_REQUIRE(!adv || (c->if_b && c->if_upwind) || g->n_iface == 0, RB_E_ARG,
                "reyna_b200_assemble: advection given without interior-face samples / upwind flags");
     if (g->n_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
     AsmArgs A;
     memset(&A, 0, sizeof(A));
     A.g = *g;
@@ -511,16 +601,28 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
     A.data = data;
     A.load = load;
     A.zero_count = reinterpret_cast<unsigned long long*>(zero_count);
-    cudaStream_t st = (cudaStream_t)stream;
     A.has_dups = s->n_dup_items > 0;
-    // elements per CTA: fill one pass of items (the heavier phase) to ~90 %
+    // prepass tables (16-byte aligned slices of the workspace)
+    uintptr_t w = ((uintptr_t)workspace + 15) & ~(uintptr_t)15;
+    ElemBox* ebox = reinterpret_cast<ElemBox*>(w);
+    double* fsigma = reinterpret_cast<double*>(w + sizeof(ElemBox) * (size_t)(g->n_elem > 0 ? g->n_elem : 1));
+    A.ebox = ebox;
+    A.fsigma = fsigma;
+    {
+        const int64_t work = g->n_elem > g->n_iface ? g->n_elem : g->n_iface;
+        const int blocks = grid_for(work, 256, kNumSMs * 8);
+        dg_prepare_kernel<<<blocks, 256, 0, st>>>(*g, (diff && g->n_iface > 0) ? c->if_a_mid : nullptr, A.sigma_pp, A.p2,
+                                                 ebox, fsigma);
+        RB_LAUNCH_CHECK("dg_prepare_kernel");
+    }
     const int rs = p == 3 ? 2 : 1;
-    const double items_per_elem = g->n_rows > 0 ? (double)s->n_items / g->n_rows : 1.0;
-    const double tris_per_elem = g->n_rows > 0 ? (double)g->n_tri / g->n_rows : 1.0;
-    const double per_elem = items_per_elem > tris_per_elem ? items_per_elem : tris_per_elem;
-    int te = (int)(0.92 * (kBD / rs) / (per_elem > 1.0 ? per_elem : 1.0));
-    te = te < 1 ? 1 : (te > 64 ? 64 : te);
-    A.te = te;
+    const double items_per_elem = (double)s->n_items / g->n_rows;
+    const double tris_per_elem = (double)g->n_tri / g->n_rows;
+    const int d = (p + 1) * (p + 2) / 2;
+    // relative cost of one item of each phase (FMA counts of the two contractions)
+    const double w_vol = tris_per_elem * qv * (d * d * (diff ? 3.0 : 1.0) + 12.0 * d);
+    const double w_face = items_per_elem * qe * (2.0 * d * d * (diff ? 2.0 : 1.0) + 30.0 * d);
+    A.te = choose_te(tris_per_elem, items_per_elem, rs, w_vol, w_face);
     switch (p) {
         case 1: return dispatch_coefs<1, 1>(A, diff, adv, st);
         case 2: return dispatch_coefs<2, 1>(A, diff, adv, st);

@@ -48,7 +48,7 @@ inline LegConst make_leg_const() {
 }
 
 // Per-element scaling derived from the Cartesian bounding box [xmin,xmax,ymin,ymax].
-struct ElemBox {
+struct __align__(16) ElemBox {
     double mx, my;       // mid point
     double ihx, ihy;     // 1 / half-extent
     double s05x, s05y;   // h^-1/2

@@ -284,24 +284,28 @@ __global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows,
         const int g0 = grp_off[e];
         const int ng = grp_off[e + 1] - g0;
         const int nb = ng + 1;
-        // block columns in ascending order with the diagonal inserted (lane 0; lists are tiny)
-        if (lane == 0) {
-            int k = 0;
-            bool placed = false;
-            for (int a = lo; a < hi; ++a) {
-                const int it = adj_item[a];
-                if (it < 0) continue;   // dup flag
-                const int o = ielem[2 * (it >> 1) + (1 - (it & 1))];
-                if (!placed && o > e) {
-                    if (k <= kMaxNb) s_nb[w][k] = e;
-                    ++k;
-                    placed = true;
-                }
-                if (k <= kMaxNb) s_nb[w][k] = o;
-                ++k;
+        // block columns in ascending order with the diagonal inserted: the (sorted) items are read one per lane and
+        // compacted with a ballot (group leaders only; "same neighbour" followers carry the dup bit)
+        int before = 0;          // leaders seen so far
+        int below = 0;           // leaders with neighbour < e (= slot of the diagonal block)
+        for (int a0 = lo; a0 < hi; a0 += 32) {
+            const int a = a0 + lane;
+            int it = -1, o = -1;
+            if (a < hi) {
+                it = adj_item[a];
+                if (it >= 0) o = ielem[2 * (it >> 1) + (1 - (it & 1))];
             }
-            if (!placed && k <= kMaxNb) s_nb[w][k] = e;
+            const bool leader = it >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, leader);
+            const unsigned mlow = __ballot_sync(0xffffffffu, leader && o < e);
+            if (leader) {
+                const int slot = before + __popc(m & ((1u << lane) - 1u)) + (o > e ? 1 : 0);
+                if (slot <= kMaxNb) s_nb[w][slot] = o;
+            }
+            before += __popc(m);
+            below += __popc(mlow);
         }
+        if (lane == 0 && below <= kMaxNb) s_nb[w][below] = e;
         __syncwarp();
         const int64_t base = (int64_t)dd * (g0 + e);
         const int rowlen = nb * d;

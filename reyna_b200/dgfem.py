@@ -348,8 +348,11 @@ class DGFEM:
         zero_count = torch.zeros(1, dtype=torch.int64, device=dev)
         _lib.check(L.reyna_b200_csr_pattern(C.byref(g), C.byref(st), p, _ptr(indptr), _ptr(indices), sp),
                    'reyna_b200_csr_pattern')
+        aws_bytes = L.reyna_b200_assemble_workspace(E, fg.n_iface)
+        aws = torch.empty(aws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(L.reyna_b200_assemble(C.byref(g), C.byref(st), C.byref(co), C.byref(q), float(self.sigma_D),
-                                         _ptr(data), _ptr(load), _ptr(zero_count), sp), 'reyna_b200_assemble')
+                                         _ptr(data), _ptr(load), _ptr(zero_count), _ptr(aws), aws_bytes, sp),
+                   'reyna_b200_assemble')
         n_bnd = int(bd['bnd_elem'].shape[0])
         spill = torch.zeros(max(1, n_bnd), **f64)
         if n_bnd:
@@ -384,14 +387,14 @@ class DGFEM:
                     structure=dict(adj_off=adj_off, adj_item=adj_item, grp_off=grp_off, n_items=st.n_items,
                                    n_groups=st.n_groups, n_dup_items=st.n_dup_items),
                     # ctypes argument blocks of the fused assembly launch (bench.py re-launches it alone for the roofline)
-                    _assemble_call=(g, st, co, q, structural_data, load, zero_count))
+                    _assemble_call=(g, st, co, q, structural_data, load, zero_count, aws, aws_bytes))
 
     def _relaunch_assemble(self, dv, stream_ptr) -> None:
         """Launch the fused volume+face assembly kernel once more on the system of the last dgfem() (measurement aid)."""
-        g, st, co, q, data, load, zero_count = dv['_assemble_call']
+        g, st, co, q, data, load, zero_count, aws, aws_bytes = dv['_assemble_call']
         _lib.check(_lib.lib().reyna_b200_assemble(C.byref(g), C.byref(st), C.byref(co), C.byref(q), float(self.sigma_D),
-                                                  _ptr(data), _ptr(load), _ptr(zero_count), stream_ptr),
-                   'reyna_b200_assemble')
+                                                  _ptr(data), _ptr(load), _ptr(zero_count), _ptr(aws), aws_bytes,
+                                                  stream_ptr), 'reyna_b200_assemble')
 
     def _solve_device(self) -> np.ndarray:
         torch = _lib.require_cuda()

@@ -7,27 +7,32 @@
 //   the scipy COO->CSR conversions and `B += ...`    main.py:319-320, 371-372, 211
 //
 // Design (B200): a CTA owns TE consecutive elements, i.e. TE consecutive block rows of B.
-//   phase A  one thread per sub-triangle: Legendre basis + gradients in registers, the d x d local block (and the load)
-//            accumulated in registers over the (p+1)^2 points, then summed per element IN TRIANGLE ORDER through a
-//            shared-memory stage (the reference's `s[:, elem] += ...` order, main.py:315).
-//   phase B  one thread per (element, interior face) item of the element->face adjacency: the diagonal part
-//            B[K,K] of the SIPG/upwind face matrix goes through the same staged per-element sum, the off-diagonal part
-//            B[K,K'] is complete after one face and is stored straight into its final CSR position.
-//            Each face is therefore visited from both of its elements, each side producing only its own block rows:
-//            no intermediate face-matrix buffer, no scatter-add, bitwise reproducible.
+//   phase A  sub-triangles: Legendre basis + gradients in registers, the d x d local block (and the load) accumulated in
+//            registers over the (p+1)^2 points, then summed per element IN TRIANGLE ORDER through a shared-memory stage
+//            (the reference's `s[:, elem] += ...` order, main.py:315).
+//   phase B  (element, interior face) items of the element->face adjacency: the diagonal part B[K,K] of the SIPG/upwind
+//            face matrix goes through the same staged per-element sum, the off-diagonal part B[K,K'] is complete after
+//            one face and is stored straight into its final CSR position.  Each face is therefore visited from both of
+//            its elements, each side producing only its own block rows: no intermediate face-matrix buffer, no
+//            scatter-add, bitwise reproducible.
 //   phase C  the summed diagonal blocks and load are written to the CSR value array / load vector.
-// Coefficient samples are q-major ([q][item]) so that the per-point loads of a warp are contiguous.
-// For d = 10 (p = 3) a thread owns half of the block rows (RS = 2) to keep the accumulators in registers; the halves are
-// assigned per half-CTA so that the compile-time row offset stays warp-uniform.
+// An item is processed by RS threads, each owning d/RS COLUMNS (trial functions) of the blocks: the FP64 accumulators are
+// what limits occupancy (8 warps per SM with a whole 6 x 6 block per thread), and a column split only duplicates the
+// basis evaluation -- the per-column quantities (a grad phi_i, b.grad phi_i, ...) are computed once.  The RS parts of an
+// item sit in different warps (part = tid / IT), so the compile-time column offset stays warp-uniform.
+// Coefficient samples are q-major ([q][item]); they travel global -> shared with per-thread cp.async so that all points
+// of an item are in flight at once without costing registers.
 #include "basis.cuh"
+#include <cuda_pipeline.h>
+#include <stdlib.h>
 
 namespace rb {
 
 constexpr int kBD = 128;   // threads per CTA
-#ifndef RB_FUSE_LIMIT
-#define RB_FUSE_LIMIT 36
+#ifndef RB_MINB
+#define RB_MINB 3
 #endif
-constexpr int kFuseLimit = RB_FUSE_LIMIT;   // accumulators per block up to which a face item forms both blocks in one sweep
+constexpr int kFuseLimit = 18;   // accumulators per block up to which a face item forms both of its blocks in one sweep
 
 struct AsmArgs {
     rb_geom g;
@@ -95,32 +100,38 @@ struct Dims {
     static constexpr int D = (P + 1) * (P + 2) / 2;
     static constexpr int DD = D * D;
     static constexpr int NV = DD + D;       // per-element accumulators in shared memory: block + load
-    static constexpr int RJ = D / RS;       // block rows per thread
+    static constexpr int CI = D / RS;       // block columns (and load rows) per thread
+    static constexpr int NA = D * CI;       // block accumulators per thread
     static constexpr int QV = (P + 1) * (P + 1);
     static constexpr int QE = P + 1;
     static constexpr int IT = kBD / RS;     // items per pass
-    static constexpr int CH = (RJ * D + RJ) > 24 ? ((RJ * D + RJ + 1) / 2 > 28 ? 22 : (RJ * D + RJ + 1) / 2)
-                                                 : (RJ * D + RJ);   // staged values per round
-    static_assert(D % RS == 0, "row split must divide the local dimension");
+    static constexpr int NTV = NA + CI;     // values a thread stages after a volume pass
+    static constexpr int CH = NTV > 24 ? ((NTV + 1) / 2 > 28 ? 22 : (NTV + 1) / 2) : NTV;   // staged values per round
+    // doubles of one staged item: (a 4, b 2, c 1, f 1) per volume point, (a 4, b 2) per face point
+    static constexpr int CV = QV * 8, CF = QE * 6;
+    static constexpr int COEF = IT * (CV > CF ? CV : CF);            // doubles of the coefficient stage
+    static constexpr int BOX = IT * 16;                              // + two ElemBox per item (own / other element)
+    static constexpr int UN = (CH * (kBD + 1)) > (COEF + BOX) ? (CH * (kBD + 1)) : (COEF + BOX);   // union with the summation stage
+    static_assert(D % RS == 0, "column split must divide the local dimension");
 };
 
-__host__ __device__ inline size_t asm_smem_bytes(int nv, int ch, int te) {
-    // s_acc [te][nv] doubles | s_stage [ch][kBD+1] doubles | 3 x [te+1] ints + [te] ints
-    return sizeof(double) * ((size_t)te * nv + (size_t)ch * (kBD + 1)) + sizeof(int) * (4 * ((size_t)te + 1));
+__host__ __device__ inline size_t asm_smem_bytes(int nv, int un, int te) {
+    // s_acc [te][nv] doubles | union { s_stage [ch][kBD+1], s_coef [IT][max(CV,CF)] } doubles | 3 x [te+1] ints + [te] ints
+    return sizeof(double) * ((size_t)te * nv + (size_t)un) + sizeof(int) * (4 * ((size_t)te + 1));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // staged, ordered per-element sum of per-thread register vectors
 // ---------------------------------------------------------------------------------------------------------------
-// vals[0 .. NT) of the thread handling item (base + it) with row part `part`; items of element seg are
-// [off[seg], off[seg+1]).  Value vv of part `part` lands at s_acc[seg*NV + dst0(part) + vv] for vv < NBLK and at
-// s_acc[seg*NV + dst1(part) + (vv-NBLK)] for the tail (load entries).
-template <int NT, int CH, int IT, int RS, int NV>
+// vals[0 .. NT) of the thread handling item (base + it) with column part `part`; items of element seg are
+// [off[seg], off[seg+1]).  Block value vv = j*CI + ii (< NBLK) lands at s_acc[seg*NV + j*D + part*CI + ii], tail value
+// NBLK + ii (load entry) at s_acc[seg*NV + D*D + part*CI + ii].  The sum over an element's items runs in item order.
+template <int NT, int NBLK, int CH, int IT, int RS, int D>
 __device__ __forceinline__ void staged_sum(const double (&vals)[NT], bool active, int base, int ne,
                                            const int* __restrict__ s_off, double* __restrict__ s_acc,
-                                           double* __restrict__ s_stage, int nblk, int dst0_stride, int dst1_base,
-                                           int dst1_stride) {
+                                           double* __restrict__ s_stage) {
     constexpr int NCH = (NT + CH - 1) / CH;
+    constexpr int CI = D / RS, NV = D * D + D;
     const int tid = threadIdx.x;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -142,10 +153,22 @@ __device__ __forceinline__ void staged_sum(const double (&vals)[NT], bool active
             hi = hi > IT ? IT : hi;
             if (lo < hi) {
                 const int vv = ch * CH + v;
-                const int dst = seg * NV + (vv < nblk ? part * dst0_stride + vv : dst1_base + part * dst1_stride + (vv - nblk));
+                int dst;
+                if (vv < NBLK) {
+                    const int j = vv / CI, ii = vv - j * CI;
+                    dst = seg * NV + j * D + part * CI + ii;
+                } else {
+                    dst = seg * NV + D * D + part * CI + (vv - NBLK);
+                }
                 double s = s_acc[dst];
                 const double* src = s_stage + v * (kBD + 1) + part * IT;
-                for (int t = lo; t < hi; ++t) s += src[t];
+                // loads batched four at a time (independent of the running sum), additions strictly in item order
+                int t = lo;
+                for (; t + 4 <= hi; t += 4) {
+                    const double x0 = src[t], x1 = src[t + 1], x2 = src[t + 2], x3 = src[t + 3];
+                    s += x0; s += x1; s += x2; s += x3;
+                }
+                for (; t < hi; ++t) s += src[t];
                 s_acc[dst] = s;
             }
         }
@@ -156,65 +179,114 @@ __device__ __forceinline__ void staged_sum(const double (&vals)[NT], bool active
 // ---------------------------------------------------------------------------------------------------------------
 // phase A: one sub-triangle
 // ---------------------------------------------------------------------------------------------------------------
-struct VolCoef {
-    double a00, a01, a10, a11, b0, b1, c, f;
-};
-
-template <bool DIFF, bool ADV>
-__device__ __forceinline__ VolCoef load_vol_coef(const AsmArgs& A, size_t m) {
-    VolCoef k;
-    k.a00 = k.a01 = k.a10 = k.a11 = k.b0 = k.b1 = 0.0;
-    if (DIFF) {
-        const double2 ar0 = __ldg(reinterpret_cast<const double2*>(A.c.vol_a) + 2 * m);
-        const double2 ar1 = __ldg(reinterpret_cast<const double2*>(A.c.vol_a) + 2 * m + 1);
-        k.a00 = ar0.x; k.a01 = ar0.y; k.a10 = ar1.x; k.a11 = ar1.y;
+// Coefficient samples travel global -> shared with per-thread cp.async (LDGSTS): all (p+1)^2 points of an item are in
+// flight at once and cost no registers.  Stage layout per point q:
+// [a row0 (16 B) x IT][a row1 x IT][b x IT][c (8 B) x IT][f x IT] -- every shared access of a warp is contiguous.
+template <int P, int RS, bool DIFF, bool ADV>
+__device__ __forceinline__ void stage_vol(const AsmArgs& A, double* __restrict__ s_coef, int lt, int part, int t) {
+    using DM = Dims<P, RS>;
+    constexpr int IT = DM::IT;
+    const size_t T = (size_t)A.g.n_tri;
+#pragma unroll
+    for (int q0 = 0; q0 < DM::QV; q0 += RS) {
+        const int q = q0 + part;                 // the parts of an item stage alternating points
+        if (q < DM::QV) {
+            const size_t m = (size_t)q * T + t;
+            double2* blk = reinterpret_cast<double2*>(s_coef + (size_t)q * IT * 8);
+            if (DIFF) {
+                __pipeline_memcpy_async(blk + lt, reinterpret_cast<const double2*>(A.c.vol_a) + 2 * m, 16);
+                __pipeline_memcpy_async(blk + IT + lt, reinterpret_cast<const double2*>(A.c.vol_a) + 2 * m + 1, 16);
+            }
+            if (ADV) __pipeline_memcpy_async(blk + 2 * IT + lt, reinterpret_cast<const double2*>(A.c.vol_b) + m, 16);
+            double* sc = s_coef + (size_t)q * IT * 8 + 6 * IT;
+            if (A.c.vol_c) __pipeline_memcpy_async(sc + lt, A.c.vol_c + m, 8);
+            if (A.c.vol_f) __pipeline_memcpy_async(sc + IT + lt, A.c.vol_f + m, 8);
+        }
     }
-    if (ADV) {
-        const double2 bb = __ldg(reinterpret_cast<const double2*>(A.c.vol_b) + m);
-        k.b0 = bb.x; k.b1 = bb.y;
-    }
-    k.c = A.c.vol_c ? __ldg(A.c.vol_c + m) : 0.0;
-    k.f = A.c.vol_f ? __ldg(A.c.vol_f + m) : 0.0;
-    return k;
 }
 
-template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void triangle_block(const AsmArgs& A, int t, double (&acc)[Dims<P, RS>::RJ * Dims<P, RS>::D + Dims<P, RS>::RJ]) {
-    using DM = Dims<P, RS>;
-    constexpr int D = DM::D, RJ = DM::RJ, J0 = PART * RJ;
-    const size_t T = (size_t)A.g.n_tri;
-    // the samples of the first point are requested before the geometry chain (tri -> nodes, tri_elem -> box) resolves
-    VolCoef cur = load_vol_coef<DIFF, ADV>(A, (size_t)t);
-    const int e = A.g.tri_elem[t];
+// The bounding-box scalings of an item's element(s) are staged next to the coefficients (8 x 16 B planes of IT entries:
+// planes 0-3 own element, 4-7 other element) and re-read from shared memory at every point instead of occupying 16-32
+// registers for the whole item.
+template <int IT>
+__device__ __forceinline__ void stage_box(const AsmArgs& A, double* __restrict__ s_box, int lt, int which, int e) {
+    const double2* src = reinterpret_cast<const double2*>(A.ebox + e);
+    double2* dst = reinterpret_cast<double2*>(s_box) + (size_t)(4 * which) * IT + lt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(dst + (size_t)k * IT, src + k, 16);
+}
+
+template <int IT, bool KEEP_IN_SMEM>
+__device__ __forceinline__ ElemBox staged_box(const double* __restrict__ s_box, int lt, int which) {
+    ElemBox b;
+    if (KEEP_IN_SMEM) {
+        // volatile: the reads stay inside the point loop (hoisted, the box would occupy 16 registers for the whole item)
+        const volatile double* src = s_box + 2 * ((size_t)(4 * which) * IT + lt);
+        b.mx = src[0]; b.my = src[1];
+        b.ihx = src[2 * IT]; b.ihy = src[2 * IT + 1];
+        b.s05x = src[4 * IT]; b.s05y = src[4 * IT + 1];
+        b.s15x = src[6 * IT]; b.s15y = src[6 * IT + 1];
+    } else {
+        const double2* src = reinterpret_cast<const double2*>(s_box) + (size_t)(4 * which) * IT + lt;
+        const double2 m = src[0], ih = src[IT], s05 = src[2 * IT], s15 = src[3 * IT];
+        b.mx = m.x; b.my = m.y; b.ihx = ih.x; b.ihy = ih.y; b.s05x = s05.x; b.s05y = s05.y; b.s15x = s15.x; b.s15y = s15.y;
+    }
+    return b;
+}
+
+struct TriGeom {
+    double2 V0, V1, V2;
+    double hdet;
+};
+
+__device__ __forceinline__ TriGeom load_tri_geom(const AsmArgs& A, int t) {
+    TriGeom g;
     const int i0 = A.g.tri[3 * (size_t)t], i1 = A.g.tri[3 * (size_t)t + 1], i2 = A.g.tri[3 * (size_t)t + 2];
-    const ElemBox bx = A.ebox[e];
-    const double2 V0 = reinterpret_cast<const double2*>(A.g.nodes)[i0];
-    const double2 V1 = reinterpret_cast<const double2*>(A.g.nodes)[i1];
-    const double2 V2 = reinterpret_cast<const double2*>(A.g.nodes)[i2];
+    g.V0 = reinterpret_cast<const double2*>(A.g.nodes)[i0];
+    g.V1 = reinterpret_cast<const double2*>(A.g.nodes)[i1];
+    g.V2 = reinterpret_cast<const double2*>(A.g.nodes)[i2];
     // |det(0.5*[V1-V0; V2-V0])| (full_assembly.py:40-41); the extra 0.5 is the `0.5 * z` of :75-77
-    const double e1x = 0.5 * (V1.x - V0.x), e1y = 0.5 * (V1.y - V0.y);
-    const double e2x = 0.5 * (V2.x - V0.x), e2y = 0.5 * (V2.y - V0.y);
-    const double hdet = 0.5 * fabs(e1x * e2y - e1y * e2x);
+    const double e1x = 0.5 * (g.V1.x - g.V0.x), e1y = 0.5 * (g.V1.y - g.V0.y);
+    const double e2x = 0.5 * (g.V2.x - g.V0.x), e2y = 0.5 * (g.V2.y - g.V0.y);
+    g.hdet = 0.5 * fabs(e1x * e2y - e1y * e2x);
+    return g;
+}
+
+// acc[j*CI + ii] += sum_q W [ grad(phi_i)^T a grad(phi_j) + (b.grad(phi_i) + c phi_i) phi_j ],  i = PART*CI + ii  (column,
+// trial), j = row (test): B[(e,j),(e,i)] of full_assembly.py:56-70 with main.py:294-299.  acc[NA + ii] += sum_q W f phi_i.
+template <int P, int RS, int PART, bool DIFF, bool ADV>
+__device__ __forceinline__ void triangle_block(const AsmArgs& A, const TriGeom& g, const double* __restrict__ s_coef,
+                                               const double* __restrict__ s_box, int lt, double (&acc)[Dims<P, RS>::NTV]) {
+    using DM = Dims<P, RS>;
+    constexpr int D = DM::D, CI = DM::CI, I0 = PART * CI, NA = DM::NA, IT = DM::IT;
+    const bool has_c = A.c.vol_c != nullptr, has_f = A.c.vol_f != nullptr;
 #pragma unroll 1
     for (int q = 0; q < DM::QV; ++q) {
-        // software pipeline: the samples of point q+1 are in flight while point q is contracted (the kernel runs at
-        // 8 warps per SM, so memory latency has to be hidden inside the thread)
-        const int qn = q + 1 < DM::QV ? q + 1 : q;
-        const VolCoef nxt = load_vol_coef<DIFF, ADV>(A, (size_t)qn * T + t);
         const double r0 = A.rvx[q], r1 = A.rvy[q];
         const double l0 = 1.0 - r0 - r1;
-        const double x = l0 * V0.x + r0 * V1.x + r1 * V2.x;
-        const double y = l0 * V0.y + r0 * V1.y + r1 * V2.y;
+        const double x = l0 * g.V0.x + r0 * g.V1.x + r1 * g.V2.x;
+        const double y = l0 * g.V0.y + r0 * g.V1.y + r1 * g.V2.y;
         double phi[D], gx[D], gy[D];
-        eval_basis<P, true>(x, y, bx, A.lc, phi, gx, gy);
-        const double W = hdet * A.wv[q];
+        eval_basis<P, true>(x, y, staged_box<IT, (RS > 1)>(s_box, lt, 0), A.lc, phi, gx, gy);
+        const double W = g.hdet * A.wv[q];
         // W folded into the coefficients once per point
-        const double a00 = W * cur.a00, a01 = W * cur.a01, a10 = W * cur.a10, a11 = W * cur.a11;
-        const double b0 = W * cur.b0, b1 = W * cur.b1, cq = W * cur.c;
-        // column (trial i) quantities u = W * grad(phi_i)^T a, s = W * (b.grad(phi_i) + c phi_i) are formed one column
-        // at a time so that only the accumulators and the basis stay live
+        const double2* blk = reinterpret_cast<const double2*>(s_coef + (size_t)q * IT * 8);
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
+        if (DIFF) {
+            const double2 r0a = blk[lt], r1a = blk[IT + lt];
+            a00 = W * r0a.x; a01 = W * r0a.y; a10 = W * r1a.x; a11 = W * r1a.y;
+        }
+        if (ADV) {
+            const double2 bb = blk[2 * IT + lt];
+            b0 = W * bb.x; b1 = W * bb.y;
+        }
+        const double* sc = s_coef + (size_t)q * IT * 8 + 6 * IT;
+        const double cq = has_c ? W * sc[lt] : 0.0;
+        // column (trial i) quantities u = W * grad(phi_i)^T a, s = W * (b.grad(phi_i) + c phi_i)
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
+        for (int ii = 0; ii < CI; ++ii) {
+            constexpr int dummy = 0; (void)dummy;
+            const int i = I0 + ii;
             double u0 = 0, u1 = 0;
             if (DIFF) {
                 u0 = fma(gx[i], a00, gy[i] * a10);
@@ -223,22 +295,21 @@ __device__ __forceinline__ void triangle_block(const AsmArgs& A, int t, double (
             double si = cq * phi[i];
             if (ADV) si = fma(b0, gx[i], fma(b1, gy[i], si));
 #pragma unroll
-            for (int jj = 0; jj < RJ; ++jj) {
-                double v = acc[jj * D + i];
+            for (int j = 0; j < D; ++j) {
+                double v = acc[j * CI + ii];
                 if (DIFF) {
-                    v = fma(u0, gx[J0 + jj], v);
-                    v = fma(u1, gy[J0 + jj], v);
+                    v = fma(u0, gx[j], v);
+                    v = fma(u1, gy[j], v);
                 }
-                v = fma(si, phi[J0 + jj], v);
-                acc[jj * D + i] = v;
+                v = fma(si, phi[j], v);
+                acc[j * CI + ii] = v;
             }
         }
-        if (A.c.vol_f) {
-            const double wf = W * cur.f;
+        if (has_f) {
+            const double wf = W * sc[IT + lt];
 #pragma unroll
-            for (int jj = 0; jj < RJ; ++jj) acc[RJ * D + jj] = fma(wf, phi[J0 + jj], acc[RJ * D + jj]);
+            for (int ii = 0; ii < CI; ++ii) acc[NA + ii] = fma(wf, phi[I0 + ii], acc[NA + ii]);
         }
-        cur = nxt;
     }
 }
 
@@ -275,6 +346,7 @@ struct FaceCoef {
     double a00, a01, a10, a11, b0, b1;
 };
 
+// straight from global memory (only for the merged "same neighbour" followers of a group, which are not staged)
 template <bool DIFF, bool ADV>
 __device__ __forceinline__ FaceCoef load_face_coef(const AsmArgs& A, size_t m) {
     FaceCoef k;
@@ -291,20 +363,57 @@ __device__ __forceinline__ FaceCoef load_face_coef(const AsmArgs& A, size_t m) {
     return k;
 }
 
-// Accumulate, for rows [J0, J0+RJ) of element e, the own-element (diagonal) block into dacc and/or the other-element
-// block into oacc.  With P_r = s_r phi_r, Q_r = -F_r/2, V_c = W s_c phi_c, U_c = sigma V_c - W F_c / 2 + gamma V_c the
-// SIPG + upwind face matrix (full_assembly.py:174-212) is B[r,c] += P_r U_c + Q_r V_c.
-template <int P, int RS, int PART, bool DIFF, bool ADV, bool DO_DIAG, bool DO_OFF>
-__device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, const ElemBox& bxe, const ElemBox& bxo,
+// stage layout per face point q: [a row0 x IT][a row1 x IT][b x IT] (16 B each)
+template <int P, int RS, bool DIFF, bool ADV>
+__device__ __forceinline__ void stage_face(const AsmArgs& A, double* __restrict__ s_coef, int lt, int part, int f) {
+    using DM = Dims<P, RS>;
+    constexpr int IT = DM::IT;
+    const size_t F = (size_t)A.g.n_iface;
+#pragma unroll
+    for (int q0 = 0; q0 < DM::QE; q0 += RS) {
+        const int q = q0 + part;
+        if (q < DM::QE) {
+            const size_t m = (size_t)q * F + f;
+            double2* blk = reinterpret_cast<double2*>(s_coef + (size_t)q * IT * 6);
+            if (DIFF) {
+                __pipeline_memcpy_async(blk + lt, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m, 16);
+                __pipeline_memcpy_async(blk + IT + lt, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m + 1, 16);
+            }
+            if (ADV) __pipeline_memcpy_async(blk + 2 * IT + lt, reinterpret_cast<const double2*>(A.c.if_b) + m, 16);
+        }
+    }
+}
+
+template <int IT, bool DIFF, bool ADV>
+__device__ __forceinline__ FaceCoef staged_face_coef(const double* __restrict__ s_coef, int lt, int q) {
+    FaceCoef k;
+    k.a00 = k.a01 = k.a10 = k.a11 = k.b0 = k.b1 = 0.0;
+    const double2* blk = reinterpret_cast<const double2*>(s_coef + (size_t)q * IT * 6);
+    if (DIFF) {
+        const double2 ar0 = blk[lt], ar1 = blk[IT + lt];
+        k.a00 = ar0.x; k.a01 = ar0.y; k.a10 = ar1.x; k.a11 = ar1.y;
+    }
+    if (ADV) {
+        const double2 bb = blk[2 * IT + lt];
+        k.b0 = bb.x; k.b1 = bb.y;
+    }
+    return k;
+}
+
+// Accumulate, for columns [I0, I0+CI) and all rows of element e, the own-element (diagonal) block into dacc and/or the
+// other-element block into oacc.  With P_r = s_r phi_r, Q_r = -F_r/2, V_c = W s_c phi_c, U_c = (sigma + gamma) V_c - W F_c / 2
+// the SIPG + upwind face matrix (full_assembly.py:174-212) is B[r,c] += P_r U_c + Q_r V_c.
+template <int P, int RS, int PART, bool DIFF, bool ADV, bool DO_DIAG, bool DO_OFF, bool STAGED>
+__device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, const double* __restrict__ s_coef,
+                                            const double* __restrict__ s_box, int lt,
                                             double* __restrict__ dacc, double* __restrict__ oacc) {
     using DM = Dims<P, RS>;
-    constexpr int D = DM::D, RJ = DM::RJ, J0 = PART * RJ;
+    constexpr int D = DM::D, CI = DM::CI, I0 = PART * CI;
     const size_t F = (size_t)A.g.n_iface;
-    FaceCoef cur = load_face_coef<DIFF, ADV>(A, (size_t)c.f);
 #pragma unroll 1
     for (int q = 0; q < DM::QE; ++q) {
-        const int qn = q + 1 < DM::QE ? q + 1 : q;
-        const FaceCoef nxt = load_face_coef<DIFF, ADV>(A, (size_t)qn * F + c.f);
+        const FaceCoef cur = STAGED ? staged_face_coef<DM::IT, DIFF, ADV>(s_coef, lt, q)
+                                    : load_face_coef<DIFF, ADV>(A, (size_t)q * F + c.f);
         const double x = c.mid.x + A.xe[q] * c.tan.x;
         const double y = c.mid.y + A.xe[q] * c.tan.y;
         const double W = c.De * A.we[q];
@@ -321,115 +430,134 @@ __device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, 
         const double hw0 = -0.5 * W * atn0, hw1 = -0.5 * W * atn1;     // -W/2 * a^T n
         const double sg = c.sigma + gamma;
         double phi[D], gx[D], gy[D];
-        eval_basis<P, DIFF>(x, y, bxe, A.lc, phi, gx, gy);
-        double Pr[RJ], Qr[RJ];
+        eval_basis<P, DIFF>(x, y, staged_box<DM::IT, (RS > 1)>(s_box, lt, 0), A.lc, phi, gx, gy);
+        double Pr[D], Qr[D];
 #pragma unroll
-        for (int jj = 0; jj < RJ; ++jj) {
-            Pr[jj] = c.sgn * phi[J0 + jj];
-            if (DIFF) Qr[jj] = -0.5 * (atn0 * gx[J0 + jj] + atn1 * gy[J0 + jj]);
+        for (int j = 0; j < D; ++j) {
+            Pr[j] = c.sgn * phi[j];
+            if (DIFF) Qr[j] = -0.5 * (atn0 * gx[j] + atn1 * gy[j]);
         }
         const double Ws = W * c.sgn;
         if (DO_DIAG) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
+            for (int ii = 0; ii < CI; ++ii) {
+                const int i = I0 + ii;
                 const double Vc = Ws * phi[i];
                 double Uc = sg * Vc;
                 if (DIFF) Uc = fma(hw0, gx[i], fma(hw1, gy[i], Uc));
 #pragma unroll
-                for (int jj = 0; jj < RJ; ++jj) {
-                    double v = dacc[jj * D + i];
-                    v = fma(Pr[jj], Uc, v);
-                    if (DIFF) v = fma(Qr[jj], Vc, v);
-                    dacc[jj * D + i] = v;
+                for (int j = 0; j < D; ++j) {
+                    double v = dacc[j * CI + ii];
+                    v = fma(Pr[j], Uc, v);
+                    if (DIFF) v = fma(Qr[j], Vc, v);
+                    dacc[j * CI + ii] = v;
                 }
             }
         }
         if (DO_OFF) {
-            eval_basis<P, DIFF>(x, y, bxo, A.lc, phi, gx, gy);
+            eval_basis<P, DIFF>(x, y, staged_box<DM::IT, (RS > 1)>(s_box, lt, 1), A.lc, phi, gx, gy);
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
+            for (int ii = 0; ii < CI; ++ii) {
+                const int i = I0 + ii;
                 const double Vc = -Ws * phi[i];
                 double Uc = sg * Vc;
                 if (DIFF) Uc = fma(hw0, gx[i], fma(hw1, gy[i], Uc));
 #pragma unroll
-                for (int jj = 0; jj < RJ; ++jj) {
-                    double v = oacc[jj * D + i];
-                    v = fma(Pr[jj], Uc, v);
-                    if (DIFF) v = fma(Qr[jj], Vc, v);
-                    oacc[jj * D + i] = v;
+                for (int j = 0; j < D; ++j) {
+                    double v = oacc[j * CI + ii];
+                    v = fma(Pr[j], Uc, v);
+                    if (DIFF) v = fma(Qr[j], Vc, v);
+                    oacc[j * CI + ii] = v;
                 }
             }
         }
-        cur = nxt;
     }
 }
 
 template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void item_pass(const AsmArgs& A, int e, int k, int k_end, int slot, int nb,
-                                          int64_t row_base, double (&dacc)[Dims<P, RS>::RJ * Dims<P, RS>::D],
-                                          unsigned& zeros) {
+__device__ __forceinline__ void item_pass(const AsmArgs& A, const FaceCtx& c0, const double* __restrict__ s_coef,
+                                          double* __restrict__ s_box, int lt, int k, int k_end, int slot, int nb,
+                                          int64_t row_base, double (&dacc)[Dims<P, RS>::NA], unsigned& zeros) {
     using DM = Dims<P, RS>;
-    constexpr int D = DM::D, RJ = DM::RJ, J0 = PART * RJ;
-    constexpr bool FUSE = (RJ * D <= kFuseLimit);   // both blocks in one sweep when the accumulators fit in registers
-    const ElemBox bxe = A.ebox[e];
-    double oacc[RJ * D];
+    constexpr int D = DM::D, CI = DM::CI, I0 = PART * CI, NA = DM::NA, IT = DM::IT;
+    constexpr bool FUSE = (NA <= kFuseLimit);   // both blocks in one sweep when the accumulators fit in registers
+    double oacc[NA];
 #pragma unroll
-    for (int v = 0; v < RJ * D; ++v) oacc[v] = 0.0;
-    // a group is one item plus any following items flagged as "same neighbour" (merged blocks; non-Voronoi meshes)
-    int kk = k;
-    do {
-        const int item = A.adj_item[kk] & 0x7fffffff;
-        const FaceCtx c = face_setup<DIFF>(A, item);
-        const ElemBox bxo = A.ebox[c.o];
-        if (FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, true>(A, c, bxe, bxo, dacc, oacc);
-        else face_blocks<P, RS, PART, DIFF, ADV, false, true>(A, c, bxe, bxo, dacc, oacc);
-        ++kk;
-    } while (A.has_dups && kk < k_end && A.adj_item[kk] < 0);
-    // off-diagonal block: final after this group -> straight to its CSR slot
+    for (int v = 0; v < NA; ++v) oacc[v] = 0.0;
+    // the group leader's own face comes from the coefficient stage ...
+    if (FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, true, true>(A, c0, s_coef, s_box, lt, dacc, oacc);
+    else face_blocks<P, RS, PART, DIFF, ADV, false, true, true>(A, c0, s_coef, s_box, lt, dacc, oacc);
+    // off-diagonal block: final after this group -> straight to its CSR slot (CI consecutive columns of every row)
     const int rowlen = nb * D;
+    if (!A.has_dups) {
 #pragma unroll
-    for (int jj = 0; jj < RJ; ++jj) {
-        double* dst = A.data + row_base + (int64_t)(J0 + jj) * rowlen + (int64_t)slot * D;
-        if ((D & 1) == 0) {
+        for (int j = 0; j < D; ++j) {
+            double* dst = A.data + row_base + (int64_t)j * rowlen + (int64_t)slot * D + I0;
+            if (RS == 1 && (D & 1) == 0) {
 #pragma unroll
-            for (int i = 0; i < D; i += 2) {
-                reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(oacc[jj * D + i], oacc[jj * D + i + 1]);
-                zeros += (oacc[jj * D + i] == 0.0) + (oacc[jj * D + i + 1] == 0.0);
-            }
-        } else {
+                for (int i = 0; i < D; i += 2) {
+                    reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(oacc[j * CI + i], oacc[j * CI + i + 1]);
+                    zeros += (oacc[j * CI + i] == 0.0) + (oacc[j * CI + i + 1] == 0.0);
+                }
+            } else {
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                dst[i] = oacc[jj * D + i];
-                zeros += (oacc[jj * D + i] == 0.0);
+                for (int ii = 0; ii < CI; ++ii) {
+                    dst[ii] = oacc[j * CI + ii];
+                    zeros += (oacc[j * CI + ii] == 0.0);
+                }
             }
         }
+        if (!FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, false, true>(A, c0, s_coef, s_box, lt, dacc, dacc);
+        return;
     }
-    if (!FUSE) {
-        // second sweep for the diagonal part, after the off-diagonal registers have been retired
-        kk = k;
-        do {
-            const int item = A.adj_item[kk] & 0x7fffffff;
-            const FaceCtx c = face_setup<DIFF>(A, item);
-            face_blocks<P, RS, PART, DIFF, ADV, true, false>(A, c, bxe, bxe, dacc, dacc);
-            ++kk;
-        } while (A.has_dups && kk < k_end && A.adj_item[kk] < 0);
+    // general meshes: following items flagged "same neighbour" are merged into this block (coefficients straight from
+    // global memory; the other element's box is the same for the whole group)
+    if (!FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, false, true>(A, c0, s_coef, s_box, lt, dacc, dacc);
+    for (int kk = k + 1; kk < k_end && A.adj_item[kk] < 0; ++kk) {
+        const FaceCtx c = face_setup<DIFF>(A, A.adj_item[kk] & 0x7fffffff);
+        face_blocks<P, RS, PART, DIFF, ADV, true, true, false>(A, c, s_coef, s_box, lt, dacc, oacc);
+    }
+    for (int j = 0; j < D; ++j) {
+        double* dst = A.data + row_base + (int64_t)j * rowlen + (int64_t)slot * D + I0;
+        for (int ii = 0; ii < CI; ++ii) {
+            dst[ii] = oacc[j * CI + ii];
+            zeros += (oacc[j * CI + ii] == 0.0);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
+template <int P, int RS, int PART, bool DIFF, bool ADV>
+__device__ __forceinline__ void volume_pass(const AsmArgs& A, bool active, int t, int lt, int part,
+                                            double* __restrict__ s_coef, double* __restrict__ s_box,
+                                            double (&acc)[Dims<P, RS>::NTV]) {
+    if (active) {
+        stage_vol<P, RS, DIFF, ADV>(A, s_coef, lt, part, t);
+        if (part == 0) stage_box<Dims<P, RS>::IT>(A, s_box, lt, 0, A.g.tri_elem[t]);
+    }
+    __pipeline_commit();
+    TriGeom tg;
+    if (active) tg = load_tri_geom(A, t);           // the dependent geometry gathers overlap the async copies
+    __pipeline_wait_prior(0);
+    if (RS > 1) __syncthreads();                    // the parts of an item staged different points
+    if (active) triangle_block<P, RS, PART, DIFF, ADV>(A, tg, s_coef, s_box, lt, acc);
+}
+
 template <int P, int RS, bool DIFF, bool ADV>
-__global__ void __launch_bounds__(kBD) dg_assemble_kernel(const __grid_constant__ AsmArgs A) {
+__global__ void __launch_bounds__(kBD, (RS > 1 && P < 3) ? RB_MINB : 2) dg_assemble_kernel(const __grid_constant__ AsmArgs A) {
     using DM = Dims<P, RS>;
-    constexpr int D = DM::D, DD = DM::DD, NV = DM::NV, RJ = DM::RJ, IT = DM::IT, CH = DM::CH;
-    extern __shared__ double smem[];
+    constexpr int D = DM::D, DD = DM::DD, NV = DM::NV, NA = DM::NA, NTV = DM::NTV, IT = DM::IT, CH = DM::CH;
+    extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int ea = blockIdx.x * A.te;
     const int ne = min(A.te, A.g.n_rows - ea);
     double* s_acc = smem;                                   // [te][NV]
-    double* s_stage = s_acc + (size_t)A.te * NV;            // [CH][kBD+1]
-    int* s_toff = reinterpret_cast<int*>(s_stage + (size_t)CH * (kBD + 1));   // [te+1]
+    double* s_stage = s_acc + (size_t)A.te * NV;            // [CH][kBD+1]  summation stage, aliased with ...
+    double* s_coef = s_stage;                               // [IT][CV | CF] the coefficient stage (never live together)
+    double* s_box = s_coef + DM::COEF;                      // [8][IT] double2 planes: the items' element boxes
+    int* s_toff = reinterpret_cast<int*>(s_stage + (size_t)DM::UN);   // [te+1]
     int* s_aoff = s_toff + (A.te + 1);
     int* s_goff = s_aoff + (A.te + 1);
     int* s_dslot = s_goff + (A.te + 1);                     // [te]
@@ -443,7 +571,7 @@ __global__ void __launch_bounds__(kBD) dg_assemble_kernel(const __grid_constant_
     for (int i = tid; i < ne * NV; i += kBD) s_acc[i] = 0.0;
     __syncthreads();
 
-    const int part = tid / IT;          // warp-uniform row part
+    const int part = tid / IT;          // warp-uniform column part
     const int lt = tid - part * IT;     // item within the pass
 
     // ---- phase A: volume terms ---------------------------------------------------------------------------------
@@ -452,14 +580,13 @@ __global__ void __launch_bounds__(kBD) dg_assemble_kernel(const __grid_constant_
         for (int base = ta; base < tb; base += IT) {
             const int t = base + lt;
             const bool active = t < tb;
-            double acc[RJ * D + RJ];
+            double acc[NTV];
 #pragma unroll
-            for (int v = 0; v < RJ * D + RJ; ++v) acc[v] = 0.0;
-            if (active) {
-                if (RS == 1 || part == 0) triangle_block<P, RS, 0, DIFF, ADV>(A, t, acc);
-                else triangle_block<P, RS, RS - 1, DIFF, ADV>(A, t, acc);
-            }
-            staged_sum<RJ * D + RJ, CH, IT, RS, NV>(acc, active, base, ne, s_toff, s_acc, s_stage, RJ * D, RJ * D, DD, RJ);
+            for (int v = 0; v < NTV; ++v) acc[v] = 0.0;
+            if (RS == 1 || part == 0) volume_pass<P, RS, 0, DIFF, ADV>(A, active, t, lt, part, s_coef, s_box, acc);
+            else volume_pass<P, RS, RS - 1, DIFF, ADV>(A, active, t, lt, part, s_coef, s_box, acc);
+            __syncthreads();                                // coefficient stage -> summation stage
+            staged_sum<NTV, NA, CH, IT, RS, D>(acc, active, base, ne, s_toff, s_acc, s_stage);
         }
     }
 
@@ -469,11 +596,17 @@ __global__ void __launch_bounds__(kBD) dg_assemble_kernel(const __grid_constant_
         const int ka = s_aoff[0], kb = s_aoff[ne];
         for (int base = ka; base < kb; base += IT) {
             const int k = base + lt;
-            bool active = k < kb;
-            double dacc[RJ * D];
+            const bool in_range = k < kb;
+            const int item = in_range ? A.adj_item[k] : -1;
+            const bool active = item >= 0;                  // followers (dup bit) are handled by their group leader
+            if (active) stage_face<P, RS, DIFF, ADV>(A, s_coef, lt, part, item >> 1);
+            __pipeline_commit();
+            double dacc[NA];
 #pragma unroll
-            for (int v = 0; v < RJ * D; ++v) dacc[v] = 0.0;
-            if (active && A.adj_item[k] < 0) active = false;    // merged into the group leader
+            for (int v = 0; v < NA; ++v) dacc[v] = 0.0;
+            FaceCtx c0;
+            int seg = 0, slot = 0, nb = 1;
+            int64_t row_base = 0;
             if (active) {
                 // element of this item: last seg with s_aoff[seg] <= k
                 int lo = 0, hi = ne;
@@ -481,22 +614,33 @@ __global__ void __launch_bounds__(kBD) dg_assemble_kernel(const __grid_constant_
                     const int mid = (lo + hi) >> 1;
                     if (s_aoff[mid] <= k) lo = mid; else hi = mid;
                 }
-                const int seg = lo, e = ea + seg;
+                seg = lo;
+                const int e = ea + seg;
                 int gi = k - s_aoff[seg];
                 if (A.has_dups)
                     for (int a = s_aoff[seg]; a < k; ++a) gi -= (A.adj_item[a] < 0);
-                const int item = A.adj_item[k];
-                const int o = A.g.ielem[2 * (size_t)(item >> 1) + (1 - (item & 1))];
-                const int nb = s_goff[seg + 1] - s_goff[seg] + 1;
-                const int slot = gi + (o > e ? 1 : 0);
-                if (o < e && (RS == 1 || part == 0)) atomicAdd(&s_dslot[seg], 1);
-                const int64_t row_base = (int64_t)DD * (s_goff[seg] + e);
-                if (RS == 1 || part == 0) item_pass<P, RS, 0, DIFF, ADV>(A, e, k, s_aoff[seg + 1], slot, nb, row_base, dacc, zeros);
-                else item_pass<P, RS, RS - 1, DIFF, ADV>(A, e, k, s_aoff[seg + 1], slot, nb, row_base, dacc, zeros);
+                c0 = face_setup<DIFF>(A, item);
+                if (part == 0) {
+                    stage_box<IT>(A, s_box, lt, 0, e);
+                    stage_box<IT>(A, s_box, lt, 1, c0.o);
+                }
+                nb = s_goff[seg + 1] - s_goff[seg] + 1;
+                slot = gi + (c0.o > e ? 1 : 0);
+                if (c0.o < e && part == 0) atomicAdd(&s_dslot[seg], 1);
+                row_base = (int64_t)DD * (s_goff[seg] + e);
             }
+            __pipeline_commit();
+            __pipeline_wait_prior(0);
+            if (RS > 1) __syncthreads();
+            if (active) {
+                if (RS == 1 || part == 0)
+                    item_pass<P, RS, 0, DIFF, ADV>(A, c0, s_coef, s_box, lt, k, s_aoff[seg + 1], slot, nb, row_base, dacc, zeros);
+                else
+                    item_pass<P, RS, RS - 1, DIFF, ADV>(A, c0, s_coef, s_box, lt, k, s_aoff[seg + 1], slot, nb, row_base, dacc, zeros);
+            }
+            __syncthreads();                                // coefficient stage -> summation stage
             // merged followers stay inactive: their stage column must read as zero -> stage zeros for them
-            const bool in_range = k < kb;
-            staged_sum<RJ * D, CH, IT, RS, NV>(dacc, in_range, base, ne, s_aoff, s_acc, s_stage, RJ * D, RJ * D, DD, RJ);
+            staged_sum<NA, NA, CH, IT, RS, D>(dacc, in_range, base, ne, s_aoff, s_acc, s_stage);
         }
     }
     __syncthreads();
@@ -522,7 +666,7 @@ __global__ void __launch_bounds__(kBD) dg_assemble_kernel(const __grid_constant_
 template <int P, int RS, bool DIFF, bool ADV>
 static int launch_assemble(const AsmArgs& A, cudaStream_t st) {
     using DM = Dims<P, RS>;
-    const size_t smem = asm_smem_bytes(DM::NV, DM::CH, A.te);
+    const size_t smem = asm_smem_bytes(DM::NV, DM::UN, A.te);
     auto kern = dg_assemble_kernel<P, RS, DIFF, ADV>;
     RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (int)div_up(A.g.n_rows, A.te);
@@ -615,7 +759,10 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
                                                  ebox, fsigma);
         RB_LAUNCH_CHECK("dg_prepare_kernel");
     }
-    const int rs = p == 3 ? 2 : 1;
+    // threads per item: whole blocks per thread for p <= 2 (measured faster on B200 than column halves at 12 warps per
+    // SM, profiles/r01_assemble_tuning.md), column halves for p = 3; REYNA_B200_RS=2 selects halves at p = 2 (A/B aid)
+    int rs = p >= 3 ? 2 : 1;
+    if (const char* env = getenv("REYNA_B200_RS")) { if (atoi(env) == 2 && p == 2) rs = 2; }
     const double items_per_elem = (double)s->n_items / g->n_rows;
     const double tris_per_elem = (double)g->n_tri / g->n_rows;
     const int d = (p + 1) * (p + 2) / 2;
@@ -625,7 +772,7 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
     A.te = choose_te(tris_per_elem, items_per_elem, rs, w_vol, w_face);
     switch (p) {
         case 1: return dispatch_coefs<1, 1>(A, diff, adv, st);
-        case 2: return dispatch_coefs<2, 1>(A, diff, adv, st);
+        case 2: return rs == 2 ? dispatch_coefs<2, 2>(A, diff, adv, st) : dispatch_coefs<2, 1>(A, diff, adv, st);
         default: return dispatch_coefs<3, 2>(A, diff, adv, st);
     }
 }

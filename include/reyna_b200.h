@@ -61,6 +61,8 @@ typedef struct {
     const int32_t *bedge;      /* [n_bface][2]                      geometry.boundary_edges                  */
     const int32_t *belem;      /* [n_bface]                         geometry.boundary_edges_to_element       */
     const double  *bnorm;      /* [n_bface][2] outward              geometry.boundary_normals                */
+    const int32_t *elem_gid;   /* [n_elem] global element id of every local element (multi-GPU partitions: block columns are
+                                  ordered and numbered by it); NULL = identity                              */
 } rb_geom;
 
 /* Reference quadrature (HOST arrays; DGFEM._intialise_quadrature, main.py:233-257). */

@@ -28,7 +28,7 @@ EXPORTS = (
 class RbGeom(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_nodes", "n_elem", "n_rows", "n_tri", "n_iface", "n_bface")] + \
                [(n, C.c_void_p) for n in ("nodes", "tri", "tri_elem", "tri_off", "bbox", "area", "poly_off", "poly_vtx",
-                                          "iedge", "ielem", "inorm", "bedge", "belem", "bnorm")]
+                                          "iedge", "ielem", "inorm", "bedge", "belem", "bnorm", "elem_gid")]
 
 
 class RbQuad(C.Structure):

@@ -237,6 +237,7 @@ __device__ __forceinline__ ElemBox staged_box(const double* __restrict__ s_box, 
 struct TriGeom {
     double2 V0, V1, V2;
     double hdet;
+    ElemBox bx;      // register copy (whole-block threads, RS == 1); column-split parts read the staged copy instead
 };
 
 __device__ __forceinline__ TriGeom load_tri_geom(const AsmArgs& A, int t) {
@@ -267,7 +268,7 @@ __device__ __forceinline__ void triangle_block(const AsmArgs& A, const TriGeom& 
         const double x = l0 * g.V0.x + r0 * g.V1.x + r1 * g.V2.x;
         const double y = l0 * g.V0.y + r0 * g.V1.y + r1 * g.V2.y;
         double phi[D], gx[D], gy[D];
-        eval_basis<P, true>(x, y, staged_box<IT, (RS > 1)>(s_box, lt, 0), A.lc, phi, gx, gy);
+        eval_basis<P, true>(x, y, RS > 1 ? staged_box<IT, true>(s_box, lt, 0) : g.bx, A.lc, phi, gx, gy);
         const double W = g.hdet * A.wv[q];
         // W folded into the coefficients once per point
         const double2* blk = reinterpret_cast<const double2*>(s_coef + (size_t)q * IT * 8);
@@ -404,8 +405,8 @@ __device__ __forceinline__ FaceCoef staged_face_coef(const double* __restrict__ 
 // other-element block into oacc.  With P_r = s_r phi_r, Q_r = -F_r/2, V_c = W s_c phi_c, U_c = (sigma + gamma) V_c - W F_c / 2
 // the SIPG + upwind face matrix (full_assembly.py:174-212) is B[r,c] += P_r U_c + Q_r V_c.
 template <int P, int RS, int PART, bool DIFF, bool ADV, bool DO_DIAG, bool DO_OFF, bool STAGED>
-__device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, const double* __restrict__ s_coef,
-                                            const double* __restrict__ s_box, int lt,
+__device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, const ElemBox& bxe, const ElemBox& bxo,
+                                            const double* __restrict__ s_coef, const double* __restrict__ s_box, int lt,
                                             double* __restrict__ dacc, double* __restrict__ oacc) {
     using DM = Dims<P, RS>;
     constexpr int D = DM::D, CI = DM::CI, I0 = PART * CI;
@@ -430,7 +431,7 @@ __device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, 
         const double hw0 = -0.5 * W * atn0, hw1 = -0.5 * W * atn1;     // -W/2 * a^T n
         const double sg = c.sigma + gamma;
         double phi[D], gx[D], gy[D];
-        eval_basis<P, DIFF>(x, y, staged_box<DM::IT, (RS > 1)>(s_box, lt, 0), A.lc, phi, gx, gy);
+        eval_basis<P, DIFF>(x, y, RS > 1 ? staged_box<DM::IT, true>(s_box, lt, 0) : bxe, A.lc, phi, gx, gy);
         double Pr[D], Qr[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -455,7 +456,7 @@ __device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, 
             }
         }
         if (DO_OFF) {
-            eval_basis<P, DIFF>(x, y, staged_box<DM::IT, (RS > 1)>(s_box, lt, 1), A.lc, phi, gx, gy);
+            eval_basis<P, DIFF>(x, y, RS > 1 ? staged_box<DM::IT, true>(s_box, lt, 1) : bxo, A.lc, phi, gx, gy);
 #pragma unroll
             for (int ii = 0; ii < CI; ++ii) {
                 const int i = I0 + ii;
@@ -475,7 +476,8 @@ __device__ __forceinline__ void face_blocks(const AsmArgs& A, const FaceCtx& c, 
 }
 
 template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void item_pass(const AsmArgs& A, const FaceCtx& c0, const double* __restrict__ s_coef,
+__device__ __forceinline__ void item_pass(const AsmArgs& A, const FaceCtx& c0, const ElemBox& bxe, const ElemBox& bxo,
+                                          const double* __restrict__ s_coef,
                                           double* __restrict__ s_box, int lt, int k, int k_end, int slot, int nb,
                                           int64_t row_base, double (&dacc)[Dims<P, RS>::NA], unsigned& zeros) {
     using DM = Dims<P, RS>;
@@ -485,43 +487,43 @@ __device__ __forceinline__ void item_pass(const AsmArgs& A, const FaceCtx& c0, c
 #pragma unroll
     for (int v = 0; v < NA; ++v) oacc[v] = 0.0;
     // the group leader's own face comes from the coefficient stage ...
-    if (FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, true, true>(A, c0, s_coef, s_box, lt, dacc, oacc);
-    else face_blocks<P, RS, PART, DIFF, ADV, false, true, true>(A, c0, s_coef, s_box, lt, dacc, oacc);
+    if (FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, true, true>(A, c0, bxe, bxo, s_coef, s_box, lt, dacc, oacc);
+    else face_blocks<P, RS, PART, DIFF, ADV, false, true, true>(A, c0, bxe, bxo, s_coef, s_box, lt, dacc, oacc);
+    // ... any following items flagged "same neighbour" (merged blocks; non-Voronoi meshes) straight from global memory
+    if (A.has_dups) {
+        for (int kk = k + 1; kk < k_end && A.adj_item[kk] < 0; ++kk) {
+            const FaceCtx c = face_setup<DIFF>(A, A.adj_item[kk] & 0x7fffffff);
+            if (FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, true, false>(A, c, bxe, bxo, s_coef, s_box, lt, dacc, oacc);
+            else face_blocks<P, RS, PART, DIFF, ADV, false, true, false>(A, c, bxe, bxo, s_coef, s_box, lt, dacc, oacc);
+        }
+    }
     // off-diagonal block: final after this group -> straight to its CSR slot (CI consecutive columns of every row)
     const int rowlen = nb * D;
-    if (!A.has_dups) {
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            double* dst = A.data + row_base + (int64_t)j * rowlen + (int64_t)slot * D + I0;
-            if (RS == 1 && (D & 1) == 0) {
-#pragma unroll
-                for (int i = 0; i < D; i += 2) {
-                    reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(oacc[j * CI + i], oacc[j * CI + i + 1]);
-                    zeros += (oacc[j * CI + i] == 0.0) + (oacc[j * CI + i + 1] == 0.0);
-                }
-            } else {
-#pragma unroll
-                for (int ii = 0; ii < CI; ++ii) {
-                    dst[ii] = oacc[j * CI + ii];
-                    zeros += (oacc[j * CI + ii] == 0.0);
-                }
-            }
-        }
-        if (!FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, false, true>(A, c0, s_coef, s_box, lt, dacc, dacc);
-        return;
-    }
-    // general meshes: following items flagged "same neighbour" are merged into this block (coefficients straight from
-    // global memory; the other element's box is the same for the whole group)
-    if (!FUSE) face_blocks<P, RS, PART, DIFF, ADV, true, false, true>(A, c0, s_coef, s_box, lt, dacc, dacc);
-    for (int kk = k + 1; kk < k_end && A.adj_item[kk] < 0; ++kk) {
-        const FaceCtx c = face_setup<DIFF>(A, A.adj_item[kk] & 0x7fffffff);
-        face_blocks<P, RS, PART, DIFF, ADV, true, true, false>(A, c, s_coef, s_box, lt, dacc, oacc);
-    }
     for (int j = 0; j < D; ++j) {
         double* dst = A.data + row_base + (int64_t)j * rowlen + (int64_t)slot * D + I0;
-        for (int ii = 0; ii < CI; ++ii) {
-            dst[ii] = oacc[j * CI + ii];
-            zeros += (oacc[j * CI + ii] == 0.0);
+        if (RS == 1 && (D & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < D; i += 2) {
+                reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(oacc[j * CI + i], oacc[j * CI + i + 1]);
+                zeros += (oacc[j * CI + i] == 0.0) + (oacc[j * CI + i + 1] == 0.0);
+            }
+        } else {
+#pragma unroll
+            for (int ii = 0; ii < CI; ++ii) {
+                dst[ii] = oacc[j * CI + ii];
+                zeros += (oacc[j * CI + ii] == 0.0);
+            }
+        }
+    }
+    if (!FUSE) {
+        // second sweep for the diagonal part, after the off-diagonal registers have been retired
+        face_blocks<P, RS, PART, DIFF, ADV, true, false, true>(A, c0, bxe, bxe, s_coef, s_box, lt, dacc, dacc);
+        if (A.has_dups) {
+            for (int kk = k + 1; kk < k_end && A.adj_item[kk] < 0; ++kk) {
+                const FaceCtx c = face_setup<DIFF>(A, A.adj_item[kk] & 0x7fffffff);
+                face_blocks<P, RS, PART, DIFF, ADV, true, false, false>(A, c, bxe, bxe, s_coef, s_box, lt, dacc, dacc);
+            }
         }
     }
 }
@@ -535,11 +537,14 @@ __device__ __forceinline__ void volume_pass(const AsmArgs& A, bool active, int t
                                             double (&acc)[Dims<P, RS>::NTV]) {
     if (active) {
         stage_vol<P, RS, DIFF, ADV>(A, s_coef, lt, part, t);
-        if (part == 0) stage_box<Dims<P, RS>::IT>(A, s_box, lt, 0, A.g.tri_elem[t]);
+        if (RS > 1 && part == 0) stage_box<Dims<P, RS>::IT>(A, s_box, lt, 0, A.g.tri_elem[t]);
     }
     __pipeline_commit();
     TriGeom tg;
-    if (active) tg = load_tri_geom(A, t);           // the dependent geometry gathers overlap the async copies
+    if (active) {
+        tg = load_tri_geom(A, t);                   // the dependent geometry gathers overlap the async copies
+        if (RS == 1) tg.bx = A.ebox[A.g.tri_elem[t]];
+    }
     __pipeline_wait_prior(0);
     if (RS > 1) __syncthreads();                    // the parts of an item staged different points
     if (active) triangle_block<P, RS, PART, DIFF, ADV>(A, tg, s_coef, s_box, lt, acc);
@@ -605,6 +610,7 @@ __global__ void __launch_bounds__(kBD, (RS > 1 && P < 3) ? RB_MINB : 2) dg_assem
 #pragma unroll
             for (int v = 0; v < NA; ++v) dacc[v] = 0.0;
             FaceCtx c0;
+            ElemBox bxe, bxo;
             int seg = 0, slot = 0, nb = 1;
             int64_t row_base = 0;
             if (active) {
@@ -620,13 +626,18 @@ __global__ void __launch_bounds__(kBD, (RS > 1 && P < 3) ? RB_MINB : 2) dg_assem
                 if (A.has_dups)
                     for (int a = s_aoff[seg]; a < k; ++a) gi -= (A.adj_item[a] < 0);
                 c0 = face_setup<DIFF>(A, item);
-                if (part == 0) {
+                if (RS == 1) {
+                    bxe = A.ebox[e];
+                    bxo = A.ebox[c0.o];
+                } else if (part == 0) {
                     stage_box<IT>(A, s_box, lt, 0, e);
                     stage_box<IT>(A, s_box, lt, 1, c0.o);
                 }
                 nb = s_goff[seg + 1] - s_goff[seg] + 1;
-                slot = gi + (c0.o > e ? 1 : 0);
-                if (c0.o < e && part == 0) atomicAdd(&s_dslot[seg], 1);
+                // block columns are ordered by GLOBAL element id (partitions number ghosts after the owned elements)
+                const int og = A.g.elem_gid ? A.g.elem_gid[c0.o] : c0.o, eg = A.g.elem_gid ? A.g.elem_gid[e] : e;
+                slot = gi + (og > eg ? 1 : 0);
+                if (og < eg && part == 0) atomicAdd(&s_dslot[seg], 1);
                 row_base = (int64_t)DD * (s_goff[seg] + e);
             }
             __pipeline_commit();
@@ -634,9 +645,9 @@ __global__ void __launch_bounds__(kBD, (RS > 1 && P < 3) ? RB_MINB : 2) dg_assem
             if (RS > 1) __syncthreads();
             if (active) {
                 if (RS == 1 || part == 0)
-                    item_pass<P, RS, 0, DIFF, ADV>(A, c0, s_coef, s_box, lt, k, s_aoff[seg + 1], slot, nb, row_base, dacc, zeros);
+                    item_pass<P, RS, 0, DIFF, ADV>(A, c0, bxe, bxo, s_coef, s_box, lt, k, s_aoff[seg + 1], slot, nb, row_base, dacc, zeros);
                 else
-                    item_pass<P, RS, RS - 1, DIFF, ADV>(A, c0, s_coef, s_box, lt, k, s_aoff[seg + 1], slot, nb, row_base, dacc, zeros);
+                    item_pass<P, RS, RS - 1, DIFF, ADV>(A, c0, bxe, bxo, s_coef, s_box, lt, k, s_aoff[seg + 1], slot, nb, row_base, dacc, zeros);
             }
             __syncthreads();                                // coefficient stage -> summation stage
             // merged followers stay inactive: their stage column must read as zero -> stage zeros for them

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(64) dg_boundary_kernel(const __grid_constant__
     for (int a = A.adj_off[e]; a < A.adj_off[e + 1]; ++a) {
         const int it = A.adj_item[a];
         if (it < 0) continue;
-        dslot += (A.g.ielem[2 * (size_t)(it >> 1) + (1 - (it & 1))] < e);
+        const int o = A.g.ielem[2 * (size_t)(it >> 1) + (1 - (it & 1))];
+        dslot += A.g.elem_gid ? (A.g.elem_gid[o] < A.g.elem_gid[e]) : (o < e);
     }
     const int nb = A.grp_off[e + 1] - A.grp_off[e] + 1;
     const int64_t base = (int64_t)DD * (A.grp_off[e] + e) + (int64_t)dslot * D;

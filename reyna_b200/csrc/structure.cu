@@ -160,8 +160,11 @@ __global__ void adj_fill(int n_iface, int n_rows, const int32_t* __restrict__ ie
 
 // The segmented sort: one thread per element orders its (<= ~20) items by (neighbour, face); the atomic cursor order of
 // adj_fill is erased, so the layout is reproducible run to run.  Items that repeat the previous neighbour are flagged.
-__global__ void adj_sort(int n_rows, const int32_t* __restrict__ ielem, const int32_t* __restrict__ adj_off,
-                         int32_t* __restrict__ adj_item, int32_t* __restrict__ grp_cnt, int32_t* __restrict__ counts) {
+__device__ __forceinline__ int gid_of(const int32_t* __restrict__ gid, int e) { return gid ? gid[e] : e; }
+
+__global__ void adj_sort(int n_rows, const int32_t* __restrict__ ielem, const int32_t* __restrict__ gid,
+                         const int32_t* __restrict__ adj_off, int32_t* __restrict__ adj_item,
+                         int32_t* __restrict__ grp_cnt, int32_t* __restrict__ counts) {
     int dups = 0, maxlen = 0;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_rows; e += gridDim.x * blockDim.x) {
         const int lo = adj_off[e], hi = adj_off[e + 1];
@@ -171,12 +174,12 @@ __global__ void adj_sort(int n_rows, const int32_t* __restrict__ ielem, const in
         for (int a = lo + 1; a < hi; ++a) {
             const int it = adj_item[a];
             const int f = it >> 1, side = it & 1;
-            const int nb = ielem[2 * f + (1 - side)];
+            const int nb = gid_of(gid, ielem[2 * f + (1 - side)]);
             int b = a - 1;
             while (b >= lo) {
                 const int jt = adj_item[b];
                 const int jf = jt >> 1, js = jt & 1;
-                const int jn = ielem[2 * jf + (1 - js)];
+                const int jn = gid_of(gid, ielem[2 * jf + (1 - js)]);
                 if (jn > nb || (jn == nb && jt > it)) {
                     adj_item[b + 1] = jt;
                     --b;
@@ -189,7 +192,7 @@ __global__ void adj_sort(int n_rows, const int32_t* __restrict__ ielem, const in
         int groups = 0, prev = -1;
         for (int a = lo; a < hi; ++a) {
             const int it = adj_item[a];
-            const int nb = ielem[2 * (it >> 1) + (1 - (it & 1))];
+            const int nb = gid_of(gid, ielem[2 * (it >> 1) + (1 - (it & 1))]);
             if (a > lo && nb == prev) {
                 adj_item[a] = it | kDupBit;
                 ++dups;
@@ -245,7 +248,7 @@ extern "C" int reyna_b200_structure(const rb_geom* g, int has_diffusion, const u
         RB_LAUNCH_CHECK("adj_fill");
     }
     if (n > 0) {
-        adj_sort<<<eblocks, threads, 0, st>>>(n, g->ielem, s->adj_off, s->adj_item, grp_cnt, s->counts);
+        adj_sort<<<eblocks, threads, 0, st>>>(n, g->ielem, g->elem_gid, s->adj_off, s->adj_item, grp_cnt, s->counts);
         RB_LAUNCH_CHECK("adj_sort");
     }
     rc = exclusive_scan_i32(grp_cnt, s->grp_off, (int64_t)n + 1, scratch, s->counts + 1, st);
@@ -271,6 +274,7 @@ constexpr int kMaxNb = 64;   // neighbours per element held in shared memory (po
 // one warp per block row: every scalar row (e,j) of the block row has the same column list, so it is built once in
 // shared memory and streamed d times to the contiguous index range of the block row
 __global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows, int d, const int32_t* __restrict__ ielem,
+                                                                     const int32_t* __restrict__ gid,
                                                                      const int32_t* __restrict__ adj_off,
                                                                      const int32_t* __restrict__ adj_item,
                                                                      const int32_t* __restrict__ grp_off,
@@ -286,6 +290,7 @@ __global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows,
         const int nb = ng + 1;
         // block columns in ascending order with the diagonal inserted: the (sorted) items are read one per lane and
         // compacted with a ballot (group leaders only; "same neighbour" followers carry the dup bit)
+        const int eg = gid_of(gid, e);   // block columns are ordered and numbered by GLOBAL element id
         int before = 0;          // leaders seen so far
         int below = 0;           // leaders with neighbour < e (= slot of the diagonal block)
         for (int a0 = lo; a0 < hi; a0 += 32) {
@@ -293,19 +298,19 @@ __global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows,
             int it = -1, o = -1;
             if (a < hi) {
                 it = adj_item[a];
-                if (it >= 0) o = ielem[2 * (it >> 1) + (1 - (it & 1))];
+                if (it >= 0) o = gid_of(gid, ielem[2 * (it >> 1) + (1 - (it & 1))]);
             }
             const bool leader = it >= 0;
             const unsigned m = __ballot_sync(0xffffffffu, leader);
-            const unsigned mlow = __ballot_sync(0xffffffffu, leader && o < e);
+            const unsigned mlow = __ballot_sync(0xffffffffu, leader && o < eg);
             if (leader) {
-                const int slot = before + __popc(m & ((1u << lane) - 1u)) + (o > e ? 1 : 0);
+                const int slot = before + __popc(m & ((1u << lane) - 1u)) + (o > eg ? 1 : 0);
                 if (slot <= kMaxNb) s_nb[w][slot] = o;
             }
             before += __popc(m);
             below += __popc(mlow);
         }
-        if (lane == 0 && below <= kMaxNb) s_nb[w][below] = e;
+        if (lane == 0 && below <= kMaxNb) s_nb[w][below] = eg;
         __syncwarp();
         const int64_t base = (int64_t)dd * (g0 + e);
         const int rowlen = nb * d;
@@ -373,7 +378,7 @@ extern "C" int reyna_b200_csr_pattern(const rb_geom* g, const rb_structure* s, i
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_csr_pattern: polynomial degree must be 1..3");
     const int d = (p + 1) * (p + 2) / 2;
     const int blocks = grid_for(g->n_rows, kPatWarps, kNumSMs * 8);
-    csr_pattern_kernel<<<blocks, kPatWarps * 32, 0, (cudaStream_t)stream>>>(g->n_rows, d, g->ielem, s->adj_off,
+    csr_pattern_kernel<<<blocks, kPatWarps * 32, 0, (cudaStream_t)stream>>>(g->n_rows, d, g->ielem, g->elem_gid, s->adj_off,
                                                                               s->adj_item, s->grp_off, indptr, indices);
     RB_LAUNCH_CHECK("csr_pattern_kernel");
     return 0;

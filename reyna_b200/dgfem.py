@@ -141,7 +141,7 @@ class DGFEM:
         indices = dv['indices'].cpu().numpy()
         data = dv['data'].cpu().numpy()
         load = dv['load'].cpu().numpy()
-        self._B = csr_matrix((data, indices, indptr), shape=(N, N))
+        self._B = csr_matrix((data, indices, indptr), shape=(N, dv.get('n_cols', N)))
         self._L = csr_matrix(load.reshape(-1, 1))       # zero rows pruned, as main.py:218/225 leave it
         self.timings['d2h_s'] = time.perf_counter() - t0
 
@@ -263,6 +263,8 @@ class DGFEM:
             names = ('nodes', 'tri', 'tri_elem', 'tri_off', 'bbox', 'area', 'poly_off', 'poly_vtx', 'iedge', 'ielem',
                      'inorm', 'bedge', 'belem', 'bnorm')
             cache[key] = {n: torch.from_numpy(getattr(fg, n)).to(dev) for n in names}
+            gid = getattr(fg, 'elem_gid', None)      # partitions only: local -> global element id
+            cache[key]['elem_gid'] = torch.from_numpy(gid).to(dev) if gid is not None else None
         return cache[key]
 
     def _quad_struct(self) -> "_lib.RbQuad":
@@ -313,12 +315,13 @@ class DGFEM:
         """Everything from the uploaded samples to the device-resident CSR system; also used by bench.py for the
         kernel-only timing (inputs already resident in HBM)."""
         p, d = self.polydegree, self.dim_elem
-        E = fg.n_elem
-        N = E * d
+        E = fg.n_elem                              # owned + ghost elements
+        R = getattr(fg, 'n_rows', E)               # owned elements = block rows assembled here
+        N = R * d
         i32 = dict(dtype=torch.int32, device=dev)
         f64 = dict(dtype=torch.float64, device=dev)
 
-        g = _lib.RbGeom(n_nodes=fg.n_nodes, n_elem=E, n_rows=E, n_tri=fg.n_tri, n_iface=fg.n_iface, n_bface=fg.n_bface,
+        g = _lib.RbGeom(n_nodes=fg.n_nodes, n_elem=E, n_rows=R, n_tri=fg.n_tri, n_iface=fg.n_iface, n_bface=fg.n_bface,
                         **{k: _ptr(v) for k, v in gd.items()})
         co = _lib.RbCoefs(**{k: _ptr(cd.get(k)) for k in ('vol_a', 'vol_b', 'vol_c', 'vol_f', 'if_a', 'if_b', 'if_a_mid',
                                                           'if_upwind', 'bf_a', 'bf_b', 'bf_g', 'bf_a_mid')})
@@ -327,16 +330,16 @@ class DGFEM:
         has_diff = self.diffusion is not None
         # -- structure
         st = _lib.RbStructure()
-        adj_off = torch.empty(E + 1, **i32)
+        adj_off = torch.empty(R + 1, **i32)
         adj_item = torch.empty(max(1, 2 * fg.n_iface), **i32)
-        grp_off = torch.empty(E + 1, **i32)
+        grp_off = torch.empty(R + 1, **i32)
         counts = torch.empty(4, **i32)
         st.adj_off, st.adj_item, st.grp_off, st.counts = _ptr(adj_off), _ptr(adj_item), _ptr(grp_off), _ptr(counts)
-        ws_bytes = L.reyna_b200_structure_workspace(E, fg.n_iface)
+        ws_bytes = L.reyna_b200_structure_workspace(R, fg.n_iface)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(L.reyna_b200_structure(C.byref(g), int(has_diff), _ptr(cd.get('if_upwind')), C.byref(st), _ptr(ws),
                                           ws_bytes, sp), 'reyna_b200_structure')
-        nnz = d * d * (E + st.n_groups)
+        nnz = d * d * (R + st.n_groups)
         if nnz >= 2 ** 31:
             raise _lib.ReynaB200Error(f'nnz = {nnz} does not fit the int32 CSR indices')
 
@@ -361,6 +364,9 @@ class DGFEM:
                                              _ptr(bd['flags']), _ptr(data), _ptr(load), _ptr(spill),
                                              _ptr(zero_count), sp), 'reyna_b200_boundary')
         if bool((bd['flags'] & 4).any()):
+            if getattr(fg, 'elem_gid', None) is not None:
+                raise _lib.ReynaB200Error('partitioned assembly does not mirror the reference index quirk of main.py:397-400 '
+                                          '(boundary edges that are only partly elliptic)')
             data[0] -= spill.sum()          # the reference's B[0,0] quirk (main.py:397-400)
             zero_count += (data[0] == 0).to(torch.int64)
         blocked = True
@@ -384,6 +390,7 @@ class DGFEM:
             blocked = False
         tm['nnz'] = int(nnz)
         return dict(indptr=indptr, indices=indices, data=data, load=load, blocked=blocked, n=N, d=d,
+                    n_cols=int(getattr(self.geometry, 'n_global_elements', R)) * d,
                     structure=dict(adj_off=adj_off, adj_item=adj_item, grp_off=grp_off, n_items=st.n_items,
                                    n_groups=st.n_groups, n_dup_items=st.n_dup_items),
                     # ctypes argument blocks of the fused assembly launch (bench.py re-launches it alone for the roofline)
@@ -401,6 +408,9 @@ class DGFEM:
         L = _lib.lib()
         dv = self._dev
         N, d = dv['n'], dv['d']
+        if dv.get('n_cols', N) != N:
+            raise _lib.ReynaB200Error('a partitioned system is solved through reyna_b200.distributed (halo exchange), '
+                                      'not through DGFEM.dgfem(solve=True) on one rank')
         dev = dv['data'].device
         so = self.solver_options
         method = so.get('method', 'auto')

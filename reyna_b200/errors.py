@@ -61,7 +61,7 @@ def dg_errors(dg, exact_solution, grad_exact_solution=None, div_advection=None):
         gd = dg._device_geometry(torch, dev, fg)
         dt = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in host.items()}
         g = _lib.RbGeom(n_nodes=fg.n_nodes, n_elem=fg.n_elem, n_rows=fg.n_elem, n_tri=fg.n_tri, n_iface=fg.n_iface,
-                        n_bface=fg.n_bface, **{k: v.data_ptr() for k, v in gd.items()})
+                        n_bface=fg.n_bface, **{k: (v.data_ptr() if v is not None else None) for k, v in gd.items()})
         es = _lib.RbErrSamples(**{k: (dt[k].data_ptr() if k in dt else None)
                                   for k in ('vol_u', 'vol_gu', 'vol_a', 'vol_c0', 'if_a_mid', 'if_b', 'bf_u', 'bf_a_mid',
                                             'bf_b', 'bf_flags')})

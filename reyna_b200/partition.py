@@ -1,0 +1,158 @@
+"""Element partitioning for the multi-GPU path (one process per GPU).
+
+The reference is a single-process program; this module is new.  Elements are split into contiguous index ranges (the
+benchmark meshes are numbered along a Morton curve, so a range is a compact patch; ``morton_partition_order`` gives the
+permutation for arbitrary meshes).  Rank r owns the block rows of its elements:
+
+* volume, boundary-face and interior-face terms of an owned element are computed by its owner only -- a face cut by the
+  partition is visited from both sides, each rank producing just its own rows, so the ASSEMBLY needs no collective at all
+  (the read-only geometry of the neighbouring "ghost" elements is replicated at partition time);
+* the Krylov solver needs, per SpMV, the solution coefficients of the ghost elements: ``HaloPlan`` lists, per peer rank,
+  which owned elements to send and where the received ghosts go (both sorted by global element id, so the plans of two
+  ranks agree without any negotiation).
+"""
+from __future__ import annotations
+
+import types
+import typing
+
+import numpy as np
+
+from .geometry import flat_geometry
+
+
+def partition_bounds(n_elements: int, world: int) -> np.ndarray:
+    """Contiguous, balanced element ranges: rank r owns [bounds[r], bounds[r+1])."""
+    return (np.arange(world + 1, dtype=np.int64) * n_elements) // world
+
+
+def morton_partition_order(geometry) -> np.ndarray:
+    """Permutation that numbers elements along a Z-order curve of their seed points (for meshes without locality)."""
+    from .mesh import morton_order
+    return morton_order(np.asarray(geometry.mesh.filtered_points, dtype=float))
+
+
+class PartitionedGeometry:
+    """The slice of a DGFEMGeometry that one rank needs: owned elements [0, n_rows) followed by ghost elements
+    [n_rows, n_elem) in ascending global order.  Carries the attribute names ``DGFEM`` reads."""
+
+    def __init__(self, parent, lo: int, hi: int):
+        fg = flat_geometry(parent)
+        E = fg.n_elem
+        if not (0 <= lo <= hi <= E):
+            raise ValueError("invalid element range")
+        self.parent = parent
+        self.lo, self.hi = int(lo), int(hi)
+        self.n_global_elements = E
+        R = hi - lo
+        k1, k2 = fg.ielem[:, 0].astype(np.int64), fg.ielem[:, 1].astype(np.int64)
+        own1 = (k1 >= lo) & (k1 < hi)
+        own2 = (k2 >= lo) & (k2 < hi)
+        fsel = np.flatnonzero(own1 | own2)                       # faces touching an owned element, global order kept
+        other = np.concatenate((k2[fsel][own1[fsel] & ~own2[fsel]], k1[fsel][own2[fsel] & ~own1[fsel]]))
+        ghosts = np.unique(other)                                # ascending global ids
+        gid = np.concatenate((np.arange(lo, hi, dtype=np.int64), ghosts))
+        g2l = np.full(E, -1, dtype=np.int64)
+        g2l[gid] = np.arange(gid.shape[0])
+        self.ghost_gid = ghosts
+        self.elem_gid = gid
+
+        tsel = slice(int(fg.tri_off[lo]), int(fg.tri_off[hi]))
+        bsel = np.flatnonzero((fg.belem >= lo) & (fg.belem < hi))
+        poly_cnt = np.diff(fg.poly_off)[gid]
+        poly_off = np.zeros(gid.shape[0] + 1, dtype=np.int64)
+        np.cumsum(poly_cnt, out=poly_off[1:])
+        starts = fg.poly_off[gid].astype(np.int64)
+        poly_idx = np.repeat(starts - poly_off[:-1], poly_cnt) + np.arange(int(poly_off[-1]), dtype=np.int64)
+
+        f = types.SimpleNamespace(
+            n_nodes=fg.n_nodes, n_elem=int(gid.shape[0]), n_rows=int(R), n_tri=int(tsel.stop - tsel.start),
+            n_iface=int(fsel.shape[0]), n_bface=int(bsel.shape[0]),
+            nodes=fg.nodes,
+            tri=np.ascontiguousarray(fg.tri[tsel]),
+            tri_elem=(fg.tri_elem[tsel].astype(np.int64) - lo).astype(np.int32),
+            tri_off=(fg.tri_off[lo:hi + 1].astype(np.int64) - int(fg.tri_off[lo])).astype(np.int32),
+            bbox=np.ascontiguousarray(fg.bbox[gid]), area=np.ascontiguousarray(fg.area[gid]),
+            poly_off=poly_off.astype(np.int32), poly_vtx=np.ascontiguousarray(fg.poly_vtx[poly_idx]),
+            iedge=np.ascontiguousarray(fg.iedge[fsel]),
+            ielem=np.ascontiguousarray(np.column_stack((g2l[k1[fsel]], g2l[k2[fsel]])).astype(np.int32)),
+            inorm=np.ascontiguousarray(fg.inorm[fsel]),
+            bedge=np.ascontiguousarray(fg.bedge[bsel]),
+            belem=(fg.belem[bsel].astype(np.int64) - lo).astype(np.int32),
+            bnorm=np.ascontiguousarray(fg.bnorm[bsel]),
+            elem_gid=gid.astype(np.int32),
+        )
+        self._rb_flat = f
+        self.face_gid = fsel
+        self.bface_gid = bsel
+        # attribute names DGFEM / BoundaryInformation read
+        self.nodes = fg.nodes
+        self.n_elements = int(R)
+        self.h = parent.h
+        self.boundary_edges = f.bedge
+        self.boundary_edges_to_element = f.belem
+        self.boundary_normals = f.bnorm
+        self.interior_edges = f.iedge
+        self.mesh = getattr(parent, "mesh", None)
+
+
+def partition_geometry(geometry, lo: int, hi: int) -> PartitionedGeometry:
+    return PartitionedGeometry(geometry, lo, hi)
+
+
+class HaloPlan:
+    """Who sends which owned elements to whom, and where received ghosts land (element granularity; the solver moves
+    ``d`` coefficients per element).  ``send[q]`` = local indices of owned elements rank q needs, ascending global id;
+    ``recv[q]`` = local ghost indices (>= n_rows) filled by rank q, ascending global id."""
+
+    def __init__(self, geometry, bounds: np.ndarray, rank: int):
+        fg = flat_geometry(geometry)
+        bounds = np.asarray(bounds, dtype=np.int64)
+        world = bounds.shape[0] - 1
+        self.rank, self.world = int(rank), int(world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        k1, k2 = fg.ielem[:, 0].astype(np.int64), fg.ielem[:, 1].astype(np.int64)
+        o1 = np.searchsorted(bounds, k1, side="right") - 1          # owner rank of each face side
+        o2 = np.searchsorted(bounds, k2, side="right") - 1
+        cut = o1 != o2
+        a = np.concatenate((k1[cut], k2[cut]))                       # element ...
+        oa = np.concatenate((o1[cut], o2[cut]))                      # ... its owner ...
+        ob = np.concatenate((o2[cut], o1[cut]))                      # ... and the rank that needs it as a ghost
+        self.send: typing.Dict[int, np.ndarray] = {}
+        self.recv: typing.Dict[int, np.ndarray] = {}
+        mine = oa == rank
+        for q in np.unique(ob[mine]):
+            self.send[int(q)] = np.unique(a[mine & (ob == q)]) - lo
+        need = ob == rank
+        ghosts = np.unique(a[need])
+        n_rows = hi - lo
+        for q in np.unique(oa[need]):
+            g = np.unique(a[need & (oa == q)])
+            self.recv[int(q)] = n_rows + np.searchsorted(ghosts, g)
+        self.n_rows, self.n_ghost = n_rows, int(ghosts.shape[0])
+        self.ghost_gid = ghosts
+
+    def peers(self):
+        return sorted(set(self.send) | set(self.recv))
+
+    def exchange_torch(self, x, d: int, group=None):
+        """Refresh the ghost part of ``x`` ((n_rows + n_ghost) * d values, torch tensor on any device) with
+        ``torch.distributed`` point-to-point operations (gloo on CPU, NCCL on GPU)."""
+        import torch
+        import torch.distributed as dist
+        xv = x.view(-1, d)
+        ops, bufs = [], []
+        for q in self.peers():
+            if q in self.send:
+                sb = xv[torch.as_tensor(self.send[q], device=x.device)].contiguous()
+                ops.append(dist.P2POp(dist.isend, sb, q, group=group))
+            if q in self.recv:
+                rb = torch.empty((self.recv[q].shape[0], d), dtype=x.dtype, device=x.device)
+                ops.append(dist.P2POp(dist.irecv, rb, q, group=group))
+                bufs.append((q, rb))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for q, rb in bufs:
+            xv[torch.as_tensor(self.recv[q], device=x.device)] = rb
+        return x

@@ -259,3 +259,27 @@ def test_reference_api_errors_on_gpu(rb):
         dg.errors(exact_solution=lambda x: np.ones(x.shape[0]), grad_exact_solution=lambda x: np.zeros(x.shape))
     l2, dgn, h1 = dg.errors(exact_solution=lambda x: np.ones(x.shape[0]))
     assert l2 < 1e-10 and dgn < 1e-10 and h1 is None    # tests/test_DGFEM.py:85-107 constant solution
+
+
+@pytest.mark.parametrize("world,name,p", [(3, "adr", 2), (4, "variable_hyperbolic", 1), (2, "variable", 3)])
+def test_partitioned_assembly_equals_global_rows(rb, world, name, p):
+    """Multi-GPU assembly path on one device: every rank's block rows, stacked, are the global matrix BITWISE (cut faces
+    are computed from both sides, each rank keeping its own rows; columns carry global numbering)."""
+    import scipy.sparse as sps
+    from reyna_b200.partition import partition_bounds, partition_geometry
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(4096, tiles=4, seed=11), subtriangulation="fan")
+    ref = _run(rb, geo, name, p, solve=False)
+    bounds = partition_bounds(geo.n_elements, world)
+    blocks, loads = [], []
+    for r in range(world):
+        part = partition_geometry(geo, bounds[r], bounds[r + 1])
+        dg = _run(rb, part, name, p, solve=False)
+        assert dg.B.shape == ((bounds[r + 1] - bounds[r]) * dg.dim_elem, ref.dim_system)
+        blocks.append(dg.B)
+        loads.append(np.asarray(dg.L.todense()).reshape(-1))
+        with pytest.raises(rb.ReynaB200Error):
+            dg._solve_device()
+    B = sps.vstack(blocks).tocsr()
+    assert np.array_equal(B.indptr, ref.B.indptr) and np.array_equal(B.indices, ref.B.indices)
+    assert np.array_equal(B.data, ref.B.data)
+    assert np.array_equal(np.concatenate(loads), np.asarray(ref.L.todense()).reshape(-1))

@@ -98,6 +98,7 @@ typedef struct {
     int32_t *adj_off;          /* [n_rows+1]   contributing (face,side) items per row element                 */
     int32_t *adj_item;         /* [<=2*n_iface] item = face*2+side, sorted by (neighbour, face); bit31 = same
                                   neighbour as the previous item (merged block)                              */
+    int32_t *adj_nb;           /* [<=2*n_iface] neighbour element (local id) of every item                    */
     int32_t *grp_off;          /* [n_rows+1]   distinct neighbours per row element (== adj_off without dups)  */
     int32_t *counts;           /* [4] device scratch: n_items, n_groups, n_dup_items, max_items_per_element   */
     int32_t n_items, n_groups, n_dup_items, max_items;   /* host copies, filled by reyna_b200_structure()     */

@@ -47,7 +47,7 @@ class RbErrSamples(C.Structure):
 
 
 class RbStructure(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("adj_off", "adj_item", "grp_off", "counts")] + \
+    _fields_ = [(n, C.c_void_p) for n in ("adj_off", "adj_item", "adj_nb", "grp_off", "counts")] + \
                [(n, C.c_int32) for n in ("n_items", "n_groups", "n_dup_items", "max_items")]
 
 

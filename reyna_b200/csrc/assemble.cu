@@ -22,7 +22,7 @@
 // item sit in different warps (part = tid / IT), so the compile-time column offset stays warp-uniform.
 // Coefficient samples are q-major ([q][item]); they travel global -> shared with per-thread cp.async so that all points
 // of an item are in flight at once without costing registers.
-#include "basis.cuh"
+#include "assemble_common.cuh"
 #include <cuda_pipeline.h>
 #include <stdlib.h>
 
@@ -33,26 +33,6 @@ constexpr int kBD = 128;   // threads per CTA
 #define RB_MINB 3
 #endif
 constexpr int kFuseLimit = 18;   // accumulators per block up to which a face item forms both of its blocks in one sweep
-
-struct AsmArgs {
-    rb_geom g;
-    const int32_t* adj_off;
-    const int32_t* adj_item;
-    const int32_t* grp_off;
-    rb_coefs c;
-    double wv[RB_MAX_QV], rvx[RB_MAX_QV], rvy[RB_MAX_QV];
-    double we[RB_MAX_QE], xe[RB_MAX_QE];
-    LegConst lc;
-    double sigma_pp;   // sigma_D * p^2
-    double p2;         // p^2
-    double* data;
-    double* load;
-    unsigned long long* zero_count;
-    int te;            // elements per CTA
-    int has_dups;      // adjacency contains merged (duplicate-neighbour) items
-    const ElemBox* ebox;   // [n_elem]  bounding-box scalings, written by dg_prepare_kernel
-    const double* fsigma;  // [n_iface] SIPG penalty per interior face (diffusion only), written by dg_prepare_kernel
-};
 
 // ---------------------------------------------------------------------------------------------------------------
 // prepass: per-element basis scalings and per-face penalty.  Both are needed by every (element, face) item from either
@@ -71,26 +51,35 @@ __device__ __forceinline__ double max_sub_area_g(const rb_geom& g, int e, double
 
 __global__ void __launch_bounds__(256) dg_prepare_kernel(rb_geom g, const double* __restrict__ if_a_mid, double sigma_pp,
                                                          double p2, ElemBox* __restrict__ ebox,
-                                                         double* __restrict__ fsigma) {
+                                                         double* __restrict__ fsigma, FaceRec* __restrict__ frec) {
     const int stride = gridDim.x * blockDim.x;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.n_elem; e += stride) ebox[e] = make_box(g.bbox, e);
-    if (if_a_mid == nullptr) return;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.n_iface; f += stride) {
-        const int e1 = g.ielem[2 * (size_t)f], e2 = g.ielem[2 * (size_t)f + 1];
         const double2 P0 = reinterpret_cast<const double2*>(g.nodes)[g.iedge[2 * (size_t)f]];
         const double2 P1 = reinterpret_cast<const double2*>(g.nodes)[g.iedge[2 * (size_t)f + 1]];
         const double2 n = reinterpret_cast<const double2*>(g.inorm)[f];
-        const double2 m0 = reinterpret_cast<const double2*>(if_a_mid)[2 * (size_t)f];
-        const double2 m1 = reinterpret_cast<const double2*>(if_a_mid)[2 * (size_t)f + 1];
-        // lambda = n . a(mid) . n   (full_assembly.py:140)
-        const double lam = (n.x * m0.x + n.y * m1.x) * n.x + (n.x * m0.y + n.y * m1.y) * n.y;
         const double ex = P1.x - P0.x, ey = P1.y - P0.y;
         const double tx = 0.5 * ex, ty = 0.5 * ey;
         const double De = sqrt(tx * tx + ty * ty);
-        const double a1 = g.area[e1], a2 = g.area[e2];
-        const double c1 = fmin(a1 / max_sub_area_g(g, e1, P0, ex, ey), p2);
-        const double c2 = fmin(a2 / max_sub_area_g(g, e2, P0, ex, ey), p2);
-        fsigma[f] = sigma_pp * lam * (2.0 * De) * fmax(c1 / a1, c2 / a2);   // full_assembly.py:146-148
+        double sigma = 0.0;
+        if (if_a_mid != nullptr) {
+            const int e1 = g.ielem[2 * (size_t)f], e2 = g.ielem[2 * (size_t)f + 1];
+            const double2 m0 = reinterpret_cast<const double2*>(if_a_mid)[2 * (size_t)f];
+            const double2 m1 = reinterpret_cast<const double2*>(if_a_mid)[2 * (size_t)f + 1];
+            // lambda = n . a(mid) . n   (full_assembly.py:140)
+            const double lam = (n.x * m0.x + n.y * m1.x) * n.x + (n.x * m0.y + n.y * m1.y) * n.y;
+            const double a1 = g.area[e1], a2 = g.area[e2];
+            const double c1 = fmin(a1 / max_sub_area_g(g, e1, P0, ex, ey), p2);
+            const double c2 = fmin(a2 / max_sub_area_g(g, e2, P0, ex, ey), p2);
+            sigma = sigma_pp * lam * (2.0 * De) * fmax(c1 / a1, c2 / a2);   // full_assembly.py:146-148
+            fsigma[f] = sigma;
+        }
+        FaceRec r;
+        r.midx = (P0.x + P1.x) * 0.5; r.midy = (P0.y + P1.y) * 0.5;     // same expressions as face_setup
+        r.tanx = tx; r.tany = ty;
+        r.nx = n.x; r.ny = n.y;
+        r.De = De; r.sigma = sigma;
+        frec[f] = r;
     }
 }
 
@@ -714,7 +703,8 @@ static int choose_te(double tris_per_elem, double items_per_elem, int rs, double
 }
 
 extern "C" size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface) {
-    return sizeof(ElemBox) * (size_t)(n_elem > 0 ? n_elem : 1) + sizeof(double) * (size_t)(n_iface > 0 ? n_iface : 1) + 256;
+    const size_t nf = (size_t)(n_iface > 0 ? n_iface : 1);
+    return sizeof(ElemBox) * (size_t)(n_elem > 0 ? n_elem : 1) + sizeof(FaceRec) * nf + sizeof(double) * nf + 256;
 }
 
 extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
@@ -760,14 +750,17 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
     // prepass tables (16-byte aligned slices of the workspace)
     uintptr_t w = ((uintptr_t)workspace + 15) & ~(uintptr_t)15;
     ElemBox* ebox = reinterpret_cast<ElemBox*>(w);
-    double* fsigma = reinterpret_cast<double*>(w + sizeof(ElemBox) * (size_t)(g->n_elem > 0 ? g->n_elem : 1));
+    FaceRec* frec = reinterpret_cast<FaceRec*>(w + sizeof(ElemBox) * (size_t)(g->n_elem > 0 ? g->n_elem : 1));
+    double* fsigma = reinterpret_cast<double*>(frec + (size_t)(g->n_iface > 0 ? g->n_iface : 1));
     A.ebox = ebox;
     A.fsigma = fsigma;
+    A.frec = frec;
+    A.adj_nb = s->adj_nb;
     {
         const int64_t work = g->n_elem > g->n_iface ? g->n_elem : g->n_iface;
         const int blocks = grid_for(work, 256, kNumSMs * 8);
         dg_prepare_kernel<<<blocks, 256, 0, st>>>(*g, (diff && g->n_iface > 0) ? c->if_a_mid : nullptr, A.sigma_pp, A.p2,
-                                                 ebox, fsigma);
+                                                 ebox, fsigma, frec);
         RB_LAUNCH_CHECK("dg_prepare_kernel");
     }
     // threads per item: whole blocks per thread for p <= 2 (measured faster on B200 than column halves at 12 warps per
@@ -781,6 +774,11 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
     const double w_vol = tris_per_elem * qv * (d * d * (diff ? 3.0 : 1.0) + 12.0 * d);
     const double w_face = items_per_elem * qe * (2.0 * d * d * (diff ? 2.0 : 1.0) + 30.0 * d);
     A.te = choose_te(tris_per_elem, items_per_elem, rs, w_vol, w_face);
+    // default: the element-streaming kernel (assemble_elem.cu) for p <= 2, the CTA-cooperative kernel of this file for p = 3
+    // (measured on B200); REYNA_B200_KERNEL=cta|elem forces one of them (A/B aid)
+    const char* kenv = getenv("REYNA_B200_KERNEL");
+    const bool use_elem = kenv ? strcmp(kenv, "elem") == 0 : p <= 2;
+    if (use_elem) return launch_assemble_elem(A, p, diff, adv, st);
     switch (p) {
         case 1: return dispatch_coefs<1, 1>(A, diff, adv, st);
         case 2: return rs == 2 ? dispatch_coefs<2, 2>(A, diff, adv, st) : dispatch_coefs<2, 1>(A, diff, adv, st);

@@ -1,0 +1,43 @@
+// Shared declarations of the DG assembly kernels (assemble.cu: CTA-cooperative kernel, assemble_elem.cu: element-streaming
+// kernel).
+#pragma once
+#include "basis.cuh"
+
+namespace rb {
+
+// per-face record written by dg_prepare_kernel: everything an (element, face) item needs besides the coefficient samples
+struct __align__(16) FaceRec {
+    double midx, midy;   // edge mid point
+    double tanx, tany;   // (P1 - P0) / 2
+    double nx, ny;       // unit normal K1 -> K2
+    double De;           // |tan| = half edge length
+    double sigma;        // SIPG penalty (0 without diffusion)
+};
+
+struct AsmArgs {
+    rb_geom g;
+    const int32_t* adj_off;
+    const int32_t* adj_item;
+    const int32_t* grp_off;
+    rb_coefs c;
+    double wv[RB_MAX_QV], rvx[RB_MAX_QV], rvy[RB_MAX_QV];
+    double we[RB_MAX_QE], xe[RB_MAX_QE];
+    LegConst lc;
+    double sigma_pp;   // sigma_D * p^2
+    double p2;         // p^2
+    double* data;
+    double* load;
+    unsigned long long* zero_count;
+    int te;            // elements per CTA
+    int has_dups;      // adjacency contains merged (duplicate-neighbour) items
+    const ElemBox* ebox;   // [n_elem]  bounding-box scalings, written by dg_prepare_kernel
+    const double* fsigma;  // [n_iface] SIPG penalty per interior face (diffusion only), written by dg_prepare_kernel
+    const FaceRec* frec;   // [n_iface] flattened face geometry, written by dg_prepare_kernel
+    const int32_t* adj_nb; // [n_items] neighbour element of every adjacency item (rb_structure.adj_nb)
+};
+
+
+// element-streaming kernel (assemble_elem.cu)
+int launch_assemble_elem(const AsmArgs& A, int p, bool diff, bool adv, cudaStream_t st);
+
+}  // namespace rb

@@ -164,7 +164,7 @@ __device__ __forceinline__ int gid_of(const int32_t* __restrict__ gid, int e) { 
 
 __global__ void adj_sort(int n_rows, const int32_t* __restrict__ ielem, const int32_t* __restrict__ gid,
                          const int32_t* __restrict__ adj_off, int32_t* __restrict__ adj_item,
-                         int32_t* __restrict__ grp_cnt, int32_t* __restrict__ counts) {
+                         int32_t* __restrict__ adj_nb, int32_t* __restrict__ grp_cnt, int32_t* __restrict__ counts) {
     int dups = 0, maxlen = 0;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_rows; e += gridDim.x * blockDim.x) {
         const int lo = adj_off[e], hi = adj_off[e + 1];
@@ -192,7 +192,9 @@ __global__ void adj_sort(int n_rows, const int32_t* __restrict__ ielem, const in
         int groups = 0, prev = -1;
         for (int a = lo; a < hi; ++a) {
             const int it = adj_item[a];
-            const int nb = gid_of(gid, ielem[2 * (it >> 1) + (1 - (it & 1))]);
+            const int onb = ielem[2 * (it >> 1) + (1 - (it & 1))];
+            if (adj_nb) adj_nb[a] = onb;            // neighbour (local id) of every item, for the streaming assembly kernel
+            const int nb = gid_of(gid, onb);
             if (a > lo && nb == prev) {
                 adj_item[a] = it | kDupBit;
                 ++dups;
@@ -248,7 +250,7 @@ extern "C" int reyna_b200_structure(const rb_geom* g, int has_diffusion, const u
         RB_LAUNCH_CHECK("adj_fill");
     }
     if (n > 0) {
-        adj_sort<<<eblocks, threads, 0, st>>>(n, g->ielem, g->elem_gid, s->adj_off, s->adj_item, grp_cnt, s->counts);
+        adj_sort<<<eblocks, threads, 0, st>>>(n, g->ielem, g->elem_gid, s->adj_off, s->adj_item, s->adj_nb, grp_cnt, s->counts);
         RB_LAUNCH_CHECK("adj_sort");
     }
     rc = exclusive_scan_i32(grp_cnt, s->grp_off, (int64_t)n + 1, scratch, s->counts + 1, st);

@@ -332,9 +332,11 @@ class DGFEM:
         st = _lib.RbStructure()
         adj_off = torch.empty(R + 1, **i32)
         adj_item = torch.empty(max(1, 2 * fg.n_iface), **i32)
+        adj_nb = torch.empty(max(1, 2 * fg.n_iface), **i32)
         grp_off = torch.empty(R + 1, **i32)
         counts = torch.empty(4, **i32)
-        st.adj_off, st.adj_item, st.grp_off, st.counts = _ptr(adj_off), _ptr(adj_item), _ptr(grp_off), _ptr(counts)
+        st.adj_off, st.adj_item, st.adj_nb, st.grp_off, st.counts = (_ptr(adj_off), _ptr(adj_item), _ptr(adj_nb), _ptr(grp_off),
+                                                                    _ptr(counts))
         ws_bytes = L.reyna_b200_structure_workspace(R, fg.n_iface)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(L.reyna_b200_structure(C.byref(g), int(has_diff), _ptr(cd.get('if_upwind')), C.byref(st), _ptr(ws),
@@ -391,7 +393,7 @@ class DGFEM:
         tm['nnz'] = int(nnz)
         return dict(indptr=indptr, indices=indices, data=data, load=load, blocked=blocked, n=N, d=d,
                     n_cols=int(getattr(self.geometry, 'n_global_elements', R)) * d,
-                    structure=dict(adj_off=adj_off, adj_item=adj_item, grp_off=grp_off, n_items=st.n_items,
+                    structure=dict(adj_off=adj_off, adj_item=adj_item, adj_nb=adj_nb, grp_off=grp_off, n_items=st.n_items,
                                    n_groups=st.n_groups, n_dup_items=st.n_dup_items),
                     # ctypes argument blocks of the fused assembly launch (bench.py re-launches it alone for the roofline)
                     _assemble_call=(g, st, co, q, structural_data, load, zero_count, aws, aws_bytes))

@@ -704,7 +704,8 @@ static int choose_te(double tris_per_elem, double items_per_elem, int rs, double
 
 extern "C" size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface) {
     const size_t nf = (size_t)(n_iface > 0 ? n_iface : 1);
-    return sizeof(ElemBox) * (size_t)(n_elem > 0 ? n_elem : 1) + sizeof(FaceRec) * nf + sizeof(double) * nf + 256;
+    return sizeof(ElemBox) * (size_t)(n_elem > 0 ? n_elem : 1) + sizeof(FaceRec) * nf + sizeof(double) * nf +
+           sizeof(int32_t) * (size_t)(n_elem > 0 ? n_elem : 1) + 256;
 }
 
 extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
@@ -755,6 +756,7 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
     A.ebox = ebox;
     A.fsigma = fsigma;
     A.frec = frec;
+    A.perm = reinterpret_cast<int32_t*>(fsigma + (size_t)(g->n_iface > 0 ? g->n_iface : 1));
     A.adj_nb = s->adj_nb;
     {
         const int64_t work = g->n_elem > g->n_iface ? g->n_elem : g->n_iface;

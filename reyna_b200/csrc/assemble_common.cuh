@@ -34,6 +34,7 @@ struct AsmArgs {
     const double* fsigma;  // [n_iface] SIPG penalty per interior face (diffusion only), written by dg_prepare_kernel
     const FaceRec* frec;   // [n_iface] flattened face geometry, written by dg_prepare_kernel
     const int32_t* adj_nb; // [n_items] neighbour element of every adjacency item (rb_structure.adj_nb)
+    int32_t* perm;         // [n_rows] lane-balancing element order of the streaming kernel (workspace)
 };
 
 

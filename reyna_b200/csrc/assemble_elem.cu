@@ -26,7 +26,8 @@ namespace rb {
 
 namespace elem {
 
-constexpr int kBD = 128;
+constexpr int kWarp = 32;          // elements per CTA: every warp is its own CTA, so a finished warp frees its slot at once
+constexpr int kSortChunk = 512;    // elements sorted together by number of faces (lane balance vs locality)
 
 template <int P, int RS>
 struct Dims {
@@ -36,7 +37,8 @@ struct Dims {
     static constexpr int NA = D * CI;          // block accumulators per thread
     static constexpr int QV = (P + 1) * (P + 1);
     static constexpr int QE = P + 1;
-    static constexpr int NE = kBD / RS;        // elements per CTA
+    static constexpr int NE = kWarp;           // elements per CTA
+    static constexpr int BD = kWarp * RS;      // threads per CTA (RS column parts, one warp each)
     static constexpr int RD = QV < 9 ? QV : (QV == 9 ? 9 : 8);   // depth of the volume coefficient ring (points)
     static constexpr bool FUSE = NA <= 9;      // diagonal and off-diagonal block of a face in one sweep
     // 16-byte planes per thread.  volume: RD x {a0, a1, b, (c,f)} + 2 x 3 vertices ; faces: 2 x 4 record + 2 x 4 box +
@@ -48,7 +50,7 @@ struct Dims {
 };
 
 // plane `pl` of thread `tid`: consecutive threads touch consecutive 16-byte words -> conflict-free
-__device__ __forceinline__ double2* plane(double2* s, int pl, int tid) { return s + (size_t)pl * kBD + tid; }
+__device__ __forceinline__ double2* plane(double2* s, int pl, int tid) { return s + (size_t)pl * blockDim.x + tid; }
 
 template <int D>
 __device__ __forceinline__ int gid_of(const AsmArgs& A, int e) { return A.g.elem_gid ? A.g.elem_gid[e] : e; }
@@ -448,26 +450,20 @@ __device__ __forceinline__ void element_work(const AsmArgs& A, int e, double2* s
     }
 }
 
-template <int P, int RS, bool DIFF, bool ADV>
-__global__ void __launch_bounds__(kBD, 2) dg_assemble_elem_kernel(const __grid_constant__ AsmArgs A) {
-    using DM = Dims<P, RS>;
-    constexpr int NE = DM::NE;
-    extern __shared__ __align__(16) double2 smem2[];
-    __shared__ int s_hist[32], s_start[32], s_perm[NE];
+// lane balance: elements are counting-sorted by their number of face items inside chunks of kSortChunk consecutive
+// elements (descending), so that the 32 elements of a warp run loops of (almost) equal length
+__global__ void __launch_bounds__(kSortChunk) dg_sort_kernel(int n_rows, const int32_t* __restrict__ adj_off,
+                                                             int32_t* __restrict__ perm) {
+    __shared__ int s_hist[32], s_start[32];
     const int tid = threadIdx.x;
-    const int part = tid / NE;          // warp-uniform column part
-    const int le = tid - part * NE;
-    const int ea = blockIdx.x * NE;
-    const int ne = min(NE, A.g.n_rows - ea);
-
-    // counting sort of the CTA's elements by their number of face items (descending): equal loop lengths inside a warp
+    const int e = blockIdx.x * kSortChunk + tid;
     if (tid < 32) s_hist[tid] = 0;
     __syncthreads();
     int key = 0, rank = 0;
-    if (part == 0 && le < ne) {
-        const int cnt = A.adj_off[ea + le + 1] - A.adj_off[ea + le];
+    if (e < n_rows) {
+        const int cnt = adj_off[e + 1] - adj_off[e];
         key = 31 - min(cnt, 31);
-        rank = atomicAdd(&s_hist[key], 1);
+        rank = atomicAdd(&s_hist[key], 1);      // the rank inside a bin only decides WHICH lane computes an element
     }
     __syncthreads();
     if (tid == 0) {
@@ -475,11 +471,19 @@ __global__ void __launch_bounds__(kBD, 2) dg_assemble_elem_kernel(const __grid_c
         for (int b = 0; b < 32; ++b) { s_start[b] = run; run += s_hist[b]; }
     }
     __syncthreads();
-    if (part == 0 && le < ne) s_perm[s_start[key] + rank] = le;
-    __syncthreads();
-    if (le >= ne) return;
-    const int e = ea + s_perm[le];
+    if (e < n_rows) perm[blockIdx.x * kSortChunk + s_start[key] + rank] = e;
+}
 
+template <int P, int RS, bool DIFF, bool ADV>
+__global__ void __launch_bounds__(kWarp * RS, 8 / RS) dg_assemble_elem_kernel(const __grid_constant__ AsmArgs A) {
+    using DM = Dims<P, RS>;
+    extern __shared__ __align__(16) double2 smem2[];
+    const int tid = threadIdx.x;
+    const int part = tid / kWarp;       // warp-uniform column part
+    const int le = tid - part * kWarp;
+    const int idx = blockIdx.x * kWarp + le;
+    if (idx >= A.g.n_rows) return;
+    const int e = A.perm[idx];
     unsigned zeros = 0;
     if (RS == 1 || part == 0) element_work<P, RS, 0, DIFF, ADV>(A, e, smem2, tid, zeros);
     else element_work<P, RS, RS - 1, DIFF, ADV>(A, e, smem2, tid, zeros);
@@ -489,11 +493,13 @@ __global__ void __launch_bounds__(kBD, 2) dg_assemble_elem_kernel(const __grid_c
 template <int P, int RS, bool DIFF, bool ADV>
 static int launch(const AsmArgs& A, cudaStream_t st) {
     using DM = Dims<P, RS>;
-    const size_t smem = sizeof(double2) * (size_t)DM::PL * kBD;
+    const size_t smem = sizeof(double2) * (size_t)DM::PL * DM::BD;
     auto kern = dg_assemble_elem_kernel<P, RS, DIFF, ADV>;
     RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = (int)div_up(A.g.n_rows, DM::NE);
-    kern<<<blocks, kBD, smem, st>>>(A);
+    dg_sort_kernel<<<(int)div_up(A.g.n_rows, kSortChunk), kSortChunk, 0, st>>>(A.g.n_rows, A.adj_off, A.perm);
+    RB_LAUNCH_CHECK("dg_sort_kernel");
+    const int blocks = (int)div_up(A.g.n_rows, kWarp);
+    kern<<<blocks, DM::BD, smem, st>>>(A);
     RB_LAUNCH_CHECK("dg_assemble_elem_kernel");
     return 0;
 }

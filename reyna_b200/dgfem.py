@@ -191,7 +191,8 @@ class DGFEM:
             dev_t[key] = buf.to(dev, non_blocking=True)
             nbytes += buf.numel() * 8
 
-        Xv = sampling.volume_points(fg, ref2)
+        pts = sampling.cached_points(self.geometry, fg, self.element_reference_quadrature, self.edge_reference_quadrature)
+        Xv = pts['Xv']
         if self.diffusion is not None:
             put('vol_a', self.diffusion, Xv, (2, 2))
         if self.advection is not None:
@@ -202,7 +203,7 @@ class DGFEM:
             put('vol_f', self.forcing, Xv, ())
 
         if fg.n_iface:
-            mid, Xf = sampling.edge_points(fg.nodes, fg.iedge, x1)
+            mid, Xf = pts['mid_i'], pts['Xi']
             if self.diffusion is not None:
                 put('if_a', self.diffusion, Xf, (2, 2))
                 put('if_a_mid', self.diffusion, mid, (2, 2))
@@ -214,7 +215,7 @@ class DGFEM:
                 nbytes += upw.nbytes
 
         if fg.n_bface:
-            mid, Xb = sampling.edge_points(fg.nodes, fg.bedge, x1)
+            mid, Xb = pts['mid_b'], pts['Xb']
             put('bf_g', self.dirichlet_bcs, Xb, ())
             if self.diffusion is not None:
                 put('bf_a', self.diffusion, Xb, (2, 2))

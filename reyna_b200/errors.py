@@ -28,7 +28,8 @@ def dg_errors(dg, exact_solution, grad_exact_solution=None, div_advection=None):
 
     (w2, ref2), (w1, x1) = dg.element_reference_quadrature, dg.edge_reference_quadrature
     host = {}
-    Xv = sampling.volume_points(fg, ref2)
+    pts = sampling.cached_points(dg.geometry, fg, dg.element_reference_quadrature, dg.edge_reference_quadrature)
+    Xv = pts['Xv']
     host['vol_u'] = sampling.evaluate_batched(exact_solution, Xv, ())
     c0 = sampling.evaluate_batched(dg.reaction, Xv, ())
     if div_advection is not None:
@@ -38,13 +39,13 @@ def dg_errors(dg, exact_solution, grad_exact_solution=None, div_advection=None):
         host['vol_gu'] = sampling.evaluate_batched(grad_exact_solution, Xv, (2,))
         host['vol_a'] = sampling.evaluate_batched(dg.diffusion, Xv, (2, 2))
     if fg.n_iface:
-        mid, Xf = sampling.edge_points(fg.nodes, fg.iedge, x1)
+        mid, Xf = pts['mid_i'], pts['Xi']
         if dg.diffusion is not None:
             host['if_a_mid'] = sampling.evaluate_batched(dg.diffusion, mid, (2, 2))
         if dg.advection is not None:
             host['if_b'] = sampling.evaluate_batched(dg.advection, Xf, (2,))
     if fg.n_bface:
-        mid, Xb = sampling.edge_points(fg.nodes, fg.bedge, x1)
+        mid, Xb = pts['mid_b'], pts['Xb']
         host['bf_u'] = sampling.evaluate_batched(exact_solution, Xb, ())
         if dg.diffusion is not None:
             host['bf_a_mid'] = sampling.evaluate_batched(dg.diffusion, mid, (2, 2))

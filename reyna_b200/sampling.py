@@ -13,6 +13,7 @@ import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
+from numba import njit, prange
 
 _CHUNK = 1 << 17          # points per task
 _pool = None
@@ -61,25 +62,80 @@ def evaluate_batched(fn, X: np.ndarray, tail_shape: tuple, out: np.ndarray = Non
     return out
 
 
+@njit(parallel=True, cache=True, nogil=True)
+def _volume_points_kernel(nodes, tri, ref2, out):
+    Q, T = ref2.shape[0], tri.shape[0]
+    for t in prange(T):
+        i0, i1, i2 = tri[t, 0], tri[t, 1], tri[t, 2]
+        x0, y0 = nodes[i0, 0], nodes[i0, 1]
+        x1, y1 = nodes[i1, 0], nodes[i1, 1]
+        x2, y2 = nodes[i2, 0], nodes[i2, 1]
+        for q in range(Q):
+            r0, r1 = ref2[q, 0], ref2[q, 1]
+            l0 = 1.0 - r0 - r1
+            out[q, t, 0] = l0 * x0 + r0 * x1 + r1 * x2
+            out[q, t, 1] = l0 * y0 + r0 * y1 + r1 * y2
+
+
+@njit(parallel=True, cache=True, nogil=True)
+def _edge_points_kernel(nodes, edges, x1, mid, out):
+    Q, F = x1.shape[0], edges.shape[0]
+    for f in prange(F):
+        ax, ay = nodes[edges[f, 0], 0], nodes[edges[f, 0], 1]
+        bx, by = nodes[edges[f, 1], 0], nodes[edges[f, 1], 1]
+        mx, my = (ax + bx) / 2.0, (ay + by) / 2.0
+        tx, ty = 0.5 * (bx - ax), 0.5 * (by - ay)
+        mid[f, 0] = mx
+        mid[f, 1] = my
+        for q in range(Q):
+            out[q, f, 0] = x1[q] * tx + mx
+            out[q, f, 1] = x1[q] * ty + my
+
+
 def volume_points(fg, ref2: np.ndarray) -> np.ndarray:
     """(Qv*T, 2) physical volume points, q-major: X[q,t] = (1-r0-r1) V0 + r0 V1 + r1 V2 (assembly_aux.py:7-29)."""
-    V = fg.nodes[fg.tri]                                     # (T,3,2)
-    ref2 = np.asarray(ref2)
-    l0 = 1.0 - ref2[:, 0] - ref2[:, 1]
-    Q, T = ref2.shape[0], V.shape[0]
-    X = np.empty((Q, T, 2))
-    for q in range(Q):          # same operation order as the matrix product [l0, r0, r1] @ V of the reference
-        X[q] = l0[q] * V[:, 0, :] + ref2[q, 0] * V[:, 1, :] + ref2[q, 1] * V[:, 2, :]
-    return X.reshape(-1, 2)
+    ref2 = np.ascontiguousarray(ref2, dtype=np.float64)
+    out = np.empty((ref2.shape[0], fg.tri.shape[0], 2))
+    _set_numba_threads()
+    _volume_points_kernel(fg.nodes, fg.tri, ref2, out)
+    return out.reshape(-1, 2)
 
 
 def edge_points(nodes: np.ndarray, edges: np.ndarray, x1: np.ndarray):
     """(mid (F,2), X (Qe*F,2) q-major) with X[q,f] = mid + x_q * tanvec, tanvec = (P1-P0)/2 (full_assembly.py:118-121)."""
-    P0, P1 = nodes[edges[:, 0]], nodes[edges[:, 1]]
-    mid = np.ascontiguousarray((P0 + P1) / 2.0)
-    tan = 0.5 * (P1 - P0)
-    x1 = np.asarray(x1).reshape(-1)
-    X = np.empty((x1.shape[0], edges.shape[0], 2))
-    for q in range(x1.shape[0]):
-        X[q] = x1[q] * tan + mid
-    return mid, X.reshape(-1, 2)
+    x1 = np.ascontiguousarray(np.asarray(x1).reshape(-1), dtype=np.float64)
+    mid = np.empty((edges.shape[0], 2))
+    out = np.empty((x1.shape[0], edges.shape[0], 2))
+    _set_numba_threads()
+    _edge_points_kernel(nodes, np.ascontiguousarray(edges), x1, mid, out)
+    return mid, out.reshape(-1, 2)
+
+
+def _set_numba_threads() -> None:
+    import numba
+    n = min(host_threads(), numba.config.NUMBA_NUM_THREADS)
+    if numba.get_num_threads() != n:
+        numba.set_num_threads(n)
+
+
+def cached_points(geometry, fg, element_rule, edge_rule) -> dict:
+    """Physical quadrature points of a geometry for one quadrature rule: volume ``Xv``, interior faces ``(mid_i, Xi)``,
+    boundary faces ``(mid_b, Xb)``.  They depend on the mesh and the polynomial degree only, so they are computed once
+    and kept on the geometry object (repeated assemblies with changing coefficients pay for the callables only)."""
+    ref2 = np.asarray(element_rule[1])
+    x1 = np.asarray(edge_rule[1]).reshape(-1)
+    key = (ref2.shape[0], x1.shape[0])
+    cache = getattr(geometry, '_rb_points', None)
+    if cache is None:
+        cache = {}
+        try:
+            geometry._rb_points = cache
+        except Exception:   # pragma: no cover
+            pass
+    pts = cache.get(key)
+    if pts is None:
+        pts = {'Xv': volume_points(fg, ref2)}
+        pts['mid_i'], pts['Xi'] = edge_points(fg.nodes, fg.iedge, x1) if fg.n_iface else (np.zeros((0, 2)), np.zeros((0, 2)))
+        pts['mid_b'], pts['Xb'] = edge_points(fg.nodes, fg.bedge, x1) if fg.n_bface else (np.zeros((0, 2)), np.zeros((0, 2)))
+        cache[key] = pts
+    return pts

@@ -169,11 +169,30 @@ typedef struct {
 typedef int (*rb_halo_fn)(void *user, double *x_dev, void *stream);          /* refresh ghosts of x            */
 typedef int (*rb_allreduce_fn)(void *user, double *vals_dev, int n, void *stream);   /* in-place sum           */
 
+/* Multigrid preconditioner (p-multigrid over the hierarchical Legendre modes, then aggregation multigrid on the
+ * piecewise-constant level): makes the Krylov iteration count mesh independent.  The handle OWNS its device memory
+ * (cudaMalloc; the only exception to "caller-owned buffers") and keeps pointers to the fine CSR arrays, which must stay
+ * alive and must carry the STRUCTURAL block pattern produced by reyna_b200_csr_pattern (not a compacted matrix).
+ * Elements are assumed to be numbered with spatial locality (aggregates are groups of 4 consecutive elements). */
+typedef struct rb_mg rb_mg;
+typedef struct {
+    int32_t nu;                /* damped-Jacobi sweeps before and after every coarse correction (default 3)   */
+    double  omega;             /* Jacobi damping (default 0.7)                                                */
+    double  alpha;             /* scaling of the aggregation coarse corrections (default 1.8)                 */
+} rb_mg_opts;
+int reyna_b200_mg_create(int32_t n_rows_scalar, int32_t d, int32_t p, const int32_t *indptr, const int32_t *indices,
+                         const double *data, const rb_mg_opts *opts, rb_mg **out, void *stream);
+void reyna_b200_mg_destroy(rb_mg *mg);
+int reyna_b200_mg_info(const rb_mg *mg, int32_t *n_levels, int32_t *level_rows /*[16]*/, long long *level_nnz /*[16]*/);
+/* z = coarse-space correction of r (the multigrid part of the preconditioner alone; exposed for tests) */
+int reyna_b200_mg_apply(rb_mg *mg, const double *r, double *z, void *stream);
+
 size_t reyna_b200_solve_workspace(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d);
+/* mg == NULL: block-Jacobi preconditioning only. */
 int reyna_b200_solve(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d, int blocked,
                      const int32_t *indptr, const int32_t *indices, const double *data,
                      const double *rhs, double *x, const rb_solve_opts *opts, rb_solve_info *info,
-                     rb_halo_fn halo, rb_allreduce_fn allreduce, void *user,
+                     rb_halo_fn halo, rb_allreduce_fn allreduce, void *user, rb_mg *mg,
                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* y = A x on the same matrix formats (exposed for tests and for the roofline measurement of the SpMV). */

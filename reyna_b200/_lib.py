@@ -19,6 +19,7 @@ EXPORTS = (
     "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_csr_pattern",
     "reyna_b200_assemble_workspace", "reyna_b200_assemble",
     "reyna_b200_boundary", "reyna_b200_compact_workspace", "reyna_b200_compact_count", "reyna_b200_compact_fill",
+    "reyna_b200_mg_create", "reyna_b200_mg_destroy", "reyna_b200_mg_info", "reyna_b200_mg_apply",
     "reyna_b200_solve_workspace", "reyna_b200_solve", "reyna_b200_spmv", "reyna_b200_errors_workspace",
     "reyna_b200_errors", "reyna_b200_fma_probe",
     "reyna_b200_launch_count", "reyna_b200_last_error", "reyna_b200_version",
@@ -49,6 +50,10 @@ class RbErrSamples(C.Structure):
 class RbStructure(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("adj_off", "adj_item", "adj_nb", "grp_off", "counts")] + \
                [(n, C.c_int32) for n in ("n_items", "n_groups", "n_dup_items", "max_items")]
+
+
+class RbMgOpts(C.Structure):
+    _fields_ = [("nu", C.c_int32), ("omega", C.c_double), ("alpha", C.c_double)]
 
 
 class RbSolveOpts(C.Structure):
@@ -117,7 +122,15 @@ def lib() -> C.CDLL:
     L.reyna_b200_solve_workspace.argtypes = [i32, i32, i32]
     L.reyna_b200_solve.restype = C.c_int
     L.reyna_b200_solve.argtypes = [i32, i32, i32, C.c_int, vp, vp, vp, vp, vp, C.POINTER(RbSolveOpts),
-                                   C.POINTER(RbSolveInfo), vp, vp, vp, vp, C.c_size_t, vp]
+                                   C.POINTER(RbSolveInfo), vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.reyna_b200_mg_create.restype = C.c_int
+    L.reyna_b200_mg_create.argtypes = [i32, i32, i32, vp, vp, vp, C.POINTER(RbMgOpts), C.POINTER(vp), vp]
+    L.reyna_b200_mg_destroy.restype = None
+    L.reyna_b200_mg_destroy.argtypes = [vp]
+    L.reyna_b200_mg_info.restype = C.c_int
+    L.reyna_b200_mg_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_longlong)]
+    L.reyna_b200_mg_apply.restype = C.c_int
+    L.reyna_b200_mg_apply.argtypes = [vp, vp, vp, vp]
     L.reyna_b200_spmv.restype = C.c_int
     L.reyna_b200_spmv.argtypes = [i32, i32, C.c_int, vp, vp, vp, vp, vp, vp]
     L.reyna_b200_errors_workspace.restype = C.c_size_t

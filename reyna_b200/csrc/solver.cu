@@ -289,6 +289,13 @@ __global__ void __launch_bounds__(kVecThreads) k_cg_p(int n, const double* __res
         p[i] = z[i] + beta * p[i];
 }
 
+int mg_apply_add(rb_mg* mg, const double* r, double* z, cudaStream_t st);   // multigrid.cu
+
+void block_jacobi_setup_launch(int n_blocks, int d, const int32_t* indptr, const int32_t* indices, const double* data,
+                               double* minv, int* singular, cudaStream_t st) {
+    block_jacobi_setup<<<grid_for(n_blocks, 128, kNumSMs * 16), 128, 0, st>>>(n_blocks, d, indptr, indices, data, minv, singular);
+}
+
 struct Solver {
     int n, ng, d, nb;
     int64_t nnz;
@@ -308,6 +315,14 @@ struct Solver {
             int rc = allreduce(user, red, nk, (void*)st);
             if (rc) { set_error("allreduce callback failed (%d)", rc); return rc; }
         }
+        return 0;
+    }
+    rb_mg* mg = nullptr;
+    // z = M^-1 v: block Jacobi, plus the multigrid coarse-space correction when a hierarchy is attached
+    int precond(const double* v, double* z) {
+        k_precond<<<nb, kVecThreads, 0, st>>>(n, d, minv, v, z);
+        RB_LAUNCH_CHECK("k_precond");
+        if (mg) return mg_apply_add(mg, v, z, st);
         return 0;
     }
     int spmv(double* xin, double* yout) {
@@ -348,8 +363,8 @@ extern "C" int reyna_b200_spmv(int32_t n, int32_t d, int blocked, const int32_t*
 extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int blocked, const int32_t* indptr,
                                 const int32_t* indices, const double* data, const double* rhs, double* x,
                                 const rb_solve_opts* opts, rb_solve_info* info, rb_halo_fn halo,
-                                rb_allreduce_fn allreduce, void* user, void* workspace, size_t workspace_bytes,
-                                void* stream) {
+                                rb_allreduce_fn allreduce, void* user, rb_mg* mg, void* workspace,
+                                size_t workspace_bytes, void* stream) {
     (void)blocked;
     RB_REQUIRE(indptr && indices && data && rhs && x && opts && info && workspace, RB_E_ARG,
                "reyna_b200_solve: null argument");
@@ -368,6 +383,7 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     s.n = n; s.ng = n_ghost; s.d = d; s.st = st;
     s.indptr = indptr; s.indices = indices; s.data = data;
     s.halo = halo; s.allreduce = allreduce; s.user = user;
+    s.mg = mg;
     int32_t last = 0;
     RB_CUDA(cudaMemcpyAsync(&last, indptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
@@ -389,8 +405,7 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     RB_CUDA(cudaMemsetAsync(s.p, 0, full * 3, st));
     RB_CUDA(cudaMemsetAsync(s.v, 0, own, st));
 
-    block_jacobi_setup<<<grid_for(n / d, 128, kNumSMs * 16), 128, 0, st>>>(n / d, d, indptr, indices, data, s.minv,
-                                                                            s.singular);
+    block_jacobi_setup_launch(n / d, d, indptr, indices, data, s.minv, s.singular, st);
     RB_LAUNCH_CHECK("block_jacobi_setup");
 
     int rc;
@@ -409,7 +424,7 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
         k_residual0<<<nb, kVecThreads, 0, st>>>(n, d, rhs, s.r);
         RB_LAUNCH_CHECK("k_residual0");
         if (cg) {
-            k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+            if ((rc = s.precond(s.r, s.z))) return rc;
             RB_CUDA(cudaMemcpyAsync(s.p, s.z, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
             k_dots3<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, rhs, s.partial);     // (r,z), (r,r), (b,b)
         } else {
@@ -436,6 +451,7 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
         bool inner_done = false, broke = false;
         double best_rr = true_rr;
         int stale_checks = 0;
+        double checked_rr = true_rr;      // true residual at the last verification
         while (!inner_done && it < opts->max_iter) {
             const int burst = (opts->max_iter - it) < check ? (opts->max_iter - it) : check;
             for (int k = 0; k < burst; ++k) {
@@ -445,20 +461,20 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
                     if ((rc = s.reduce(1))) return rc;
                     scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
                     k_cg_xr<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.p, s.r, s.v);
-                    k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+                    if ((rc = s.precond(s.r, s.z))) return rc;
                     k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, s.partial);               // (r,z), (r,r)
                     if ((rc = s.reduce(2))) return rc;
                     scal_rho_cg<<<1, 1, 0, st>>>(s.S, s.red);
                     k_cg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.z, s.p);
                 } else {
                     k_bicg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v, s.p);
-                    k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.p, s.y);
+                    if ((rc = s.precond(s.p, s.y))) return rc;
                     if ((rc = s.spmv(s.y, s.v))) return rc;                                  // v = A y
                     k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.rhat, s.v, s.partial);            // (rhat, v)
                     if ((rc = s.reduce(1))) return rc;
                     scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
                     k_bicg_s<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v);                   // r := s
-                    k_precond<<<nb, kVecThreads, 0, st>>>(n, d, s.minv, s.r, s.z);
+                    if ((rc = s.precond(s.r, s.z))) return rc;
                     if ((rc = s.spmv(s.z, s.t))) return rc;                                  // t = A z
                     k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.r, s.partial);               // (t,s), (t,t)
                     if ((rc = s.reduce(2))) return rc;
@@ -475,9 +491,36 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
             if (!(hS[S_RR] == hS[S_RR])) { set_error("Krylov iteration produced NaN"); broke = true; break; }
             if (hS[S_RR] <= target2) inner_done = true;
             if (hS[S_BREAK] != 0.0) { broke = true; break; }
+            // Every two decades of recurrence progress the TRUE residual is verified (one SpMV).  It follows the recurrence
+            // until it reaches its rounding floor (~ cond * eps * ||b||): then it stops improving, and iterating on would
+            // only burn time -> stop there (stagnated), or restart from the true residual if it merely drifted.
+            if (!inner_done && hS[S_RR] <= 1e-4 * checked_rr) {
+                if ((rc = s.spmv(x, s.t))) return rc;
+                k_residual0<<<nb, kVecThreads, 0, st>>>(n, d, rhs, s.t);
+                k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.t, s.partial);
+                RB_LAUNCH_CHECK("true residual check");
+                if ((rc = s.reduce(1))) return rc;
+                double trr = 0.0;
+                RB_CUDA(cudaMemcpyAsync(&trr, s.red, sizeof(double), cudaMemcpyDeviceToHost, st));
+                RB_CUDA(cudaStreamSynchronize(st));
+                if (trr > 0.25 * checked_rr) { stagnated = true; break; }       // floor reached
+                checked_rr = trr;
+                if (trr > 16.0 * hS[S_RR]) break;                               // drifted: restart from the true residual
+            }
             // the recurrence residual no longer improves: hand over to the true-residual check at the loop head
             if (hS[S_RR] < 0.9 * best_rr) { best_rr = hS[S_RR]; stale_checks = 0; }
             else if (++stale_checks >= 40) break;
+        }
+        if (stagnated) {
+            // report the true residual of the final iterate
+            if ((rc = s.spmv(x, s.t))) return rc;
+            k_residual0<<<nb, kVecThreads, 0, st>>>(n, d, rhs, s.t);
+            k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.t, s.partial);
+            RB_LAUNCH_CHECK("true residual");
+            if ((rc = s.reduce(1))) return rc;
+            RB_CUDA(cudaMemcpyAsync(&true_rr, s.red, sizeof(double), cudaMemcpyDeviceToHost, st));
+            RB_CUDA(cudaStreamSynchronize(st));
+            break;
         }
         (void)broke;   // a breakdown is handled like a restart: the loop head recomputes the true residual
     }

@@ -66,7 +66,9 @@ class DGFEM:
         self.edge_reference_quadrature = None
 
         # Krylov replacement of spsolve (main.py:231)
-        self.solver_options = {'method': 'auto', 'rtol': 1e-14, 'max_iter': 200000, 'check_every': 50}
+        # 'preconditioner': 'auto' = multigrid ('mg') when diffusion is present, block Jacobi ('bj') otherwise
+        self.solver_options = {'method': 'auto', 'rtol': 1e-14, 'max_iter': 200000, 'check_every': 10,
+                               'preconditioner': 'auto', 'mg_nu': 3, 'mg_omega': 0.7, 'mg_alpha': 1.8}
         self.solve_info: typing.Optional[dict] = None
         self.timings: dict = {}
         self.device = None         # torch device; default: current CUDA device
@@ -374,6 +376,7 @@ class DGFEM:
             zero_count += (data[0] == 0).to(torch.int64)
         blocked = True
         structural_data = data
+        structural = (indptr, indices, data)        # the solver (and its multigrid hierarchy) works on the block pattern
         nz = int(zero_count.item())         # synchronises
         tm['structural_nnz'] = int(nnz)
         tm['exact_zeros'] = nz
@@ -392,7 +395,7 @@ class DGFEM:
             indptr, indices, data, nnz = indptr2, indices2, data2, nnz2
             blocked = False
         tm['nnz'] = int(nnz)
-        return dict(indptr=indptr, indices=indices, data=data, load=load, blocked=blocked, n=N, d=d,
+        return dict(indptr=indptr, indices=indices, data=data, load=load, blocked=blocked, n=N, d=d, structural=structural,
                     n_cols=int(getattr(self.geometry, 'n_global_elements', R)) * d,
                     structure=dict(adj_off=adj_off, adj_item=adj_item, adj_nb=adj_nb, grp_off=grp_off, n_items=st.n_items,
                                    n_groups=st.n_groups, n_dup_items=st.n_dup_items),
@@ -420,20 +423,41 @@ class DGFEM:
         if method == 'auto':
             method = 'cg' if self.advection is None else 'bicgstab'
         opts = _lib.RbSolveOpts(method=0 if method == 'cg' else 1, max_iter=int(so.get('max_iter', 200000)),
-                                rtol=float(so.get('rtol', 1e-12)), check_every=int(so.get('check_every', 50)))
+                                rtol=float(so.get('rtol', 1e-14)), check_every=int(so.get('check_every', 10)))
+        prec = so.get('preconditioner', 'auto')
+        if prec == 'auto':
+            prec = 'mg' if self.diffusion is not None else 'bj'
         info = _lib.RbSolveInfo()
         t0 = time.perf_counter()
+        s_indptr, s_indices, s_data = dv['structural']
+        mg = C.c_void_p(None)
+        mg_levels = None
         with torch.cuda.device(dev):
             sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            x = torch.zeros(N, dtype=torch.float64, device=dev)
-            ws_bytes = L.reyna_b200_solve_workspace(N, 0, d)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            _lib.check(L.reyna_b200_solve(N, 0, d, int(dv['blocked']), _ptr(dv['indptr']), _ptr(dv['indices']),
-                                          _ptr(dv['data']), _ptr(dv['load']), _ptr(x), C.byref(opts), C.byref(info),
-                                          None, None, None, _ptr(ws), ws_bytes, sp), 'reyna_b200_solve')
-            sol = x.cpu().numpy()
+            try:
+                if prec == 'mg':
+                    mo = _lib.RbMgOpts(nu=int(so.get('mg_nu', 3)), omega=float(so.get('mg_omega', 0.7)),
+                                       alpha=float(so.get('mg_alpha', 1.8)))
+                    _lib.check(L.reyna_b200_mg_create(N, d, self.polydegree, _ptr(s_indptr), _ptr(s_indices), _ptr(s_data),
+                                                      C.byref(mo), C.byref(mg), sp), 'reyna_b200_mg_create')
+                    nl = C.c_int32(0)
+                    rows = (C.c_int32 * 16)()
+                    L.reyna_b200_mg_info(mg, C.byref(nl), rows, None)
+                    mg_levels = [int(rows[i]) for i in range(nl.value)]
+                setup_s = time.perf_counter() - t0
+                x = torch.zeros(N, dtype=torch.float64, device=dev)
+                ws_bytes = L.reyna_b200_solve_workspace(N, 0, d)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                _lib.check(L.reyna_b200_solve(N, 0, d, 1, _ptr(s_indptr), _ptr(s_indices), _ptr(s_data), _ptr(dv['load']),
+                                              _ptr(x), C.byref(opts), C.byref(info), None, None, None, mg, _ptr(ws),
+                                              ws_bytes, sp), 'reyna_b200_solve')
+                sol = x.cpu().numpy()
+            finally:
+                if mg.value:
+                    L.reyna_b200_mg_destroy(mg)
         self.solve_info = dict(method=method, iterations=int(info.iterations), rel_residual=float(info.rel_residual),
                                converged=bool(info.converged), restarts=int(info.restarts),
+                               preconditioner=prec, mg_levels=mg_levels, setup_seconds=setup_s,
                                stagnated=bool(info.stagnated), seconds=time.perf_counter() - t0)
         self.timings['solve_s'] = self.solve_info['seconds']
         if not info.converged and not info.stagnated:

@@ -1,0 +1,100 @@
+"""The Krylov solver that replaces spsolve (main.py:231): multigrid hierarchy and cycle against a scipy restatement of the
+same algorithm, iteration counts, and the solution against SuperLU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from reyna_b200.problems import PROBLEMS
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import torch
+    assert torch.cuda.is_available()
+    import reyna_b200
+    reyna_b200.lib()
+    return reyna_b200
+
+
+@pytest.mark.parametrize("E,name,p", [(6000, "diffusion", 2), (6000, "adr", 1), (5000, "variable", 3)])
+def test_multigrid_operator_matches_scipy_restatement(rb, E, name, p):
+    import torch
+    from oracle.mg_reference import CoarseCorrection
+    from reyna_b200 import _lib
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(E, seed=7), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=p)
+    dg.add_data(**PROBLEMS[name]["data"])
+    dg.dgfem(solve=False)
+    dv = dg._dev
+    assert dv["blocked"]
+    ref = CoarseCorrection(dg.B, p)
+    L = rb.lib()
+    ip, ix, dat = dv["structural"]
+    mg = C.c_void_p(None)
+    sp_ = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    mo = _lib.RbMgOpts(nu=3, omega=0.7, alpha=1.8)
+    _lib.check(L.reyna_b200_mg_create(dv["n"], dv["d"], p, ip.data_ptr(), ix.data_ptr(), dat.data_ptr(), C.byref(mo),
+                                      C.byref(mg), sp_), "mg_create")
+    try:
+        nl = C.c_int32(0)
+        rows = (C.c_int32 * 16)()
+        nnz = (C.c_longlong * 16)()
+        L.reyna_b200_mg_info(mg, C.byref(nl), rows, nnz)
+        assert [rows[i] for i in range(nl.value)] == ref.level_sizes()
+        assert [nnz[i] for i in range(nl.value)] == [lv["A"].nnz for lv in ref.levels]
+        rng = np.random.default_rng(0)
+        for _ in range(2):
+            r = rng.standard_normal(dv["n"])
+            rt = torch.from_numpy(r).cuda()
+            zt = torch.empty_like(rt)
+            _lib.check(L.reyna_b200_mg_apply(mg, rt.data_ptr(), zt.data_ptr(), sp_), "mg_apply")
+            z = zt.cpu().numpy()
+            zr = ref.apply(r)
+            assert util.rel_l2(z, zr) <= 1e-10
+    finally:
+        L.reyna_b200_mg_destroy(mg)
+
+
+@pytest.mark.parametrize("name,p,limit", [("diffusion", 2, 450), ("adr", 2, 300), ("diffusion", 1, 450), ("adr_tensor", 3, 450)])
+def test_multigrid_iterations_are_mesh_independent(rb, name, p, limit):
+    its = []
+    for E in (4096, 16384):
+        geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(E, tiles=4, seed=3), subtriangulation="fan")
+        dg = rb.DGFEM(geo, polynomial_degree=p)
+        dg.add_data(**PROBLEMS[name]["data"])
+        dg.solver_options.update(rtol=1e-8)       # well above the kappa * eps floor of the true residual
+        dg.dgfem(solve=True)
+        assert dg.solve_info["preconditioner"] == "mg"
+        assert dg.solve_info["converged"], dg.solve_info
+        its.append(dg.solve_info["iterations"])
+    assert max(its) <= limit, its
+    assert its[1] <= 1.5 * its[0] + 20, its           # block Jacobi alone doubles here
+
+
+def test_multigrid_solution_matches_spsolve(rb):
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(16384, tiles=4, seed=5), subtriangulation="fan")
+    for name, p in (("adr", 2), ("diffusion", 2)):
+        dg = rb.DGFEM(geo, polynomial_degree=p)
+        dg.add_data(**PROBLEMS[name]["data"])
+        dg.dgfem(solve=True)
+        B, L, info = dg_oracle.assemble(geo, p, **PROBLEMS[name]["data"])
+        x = dg_oracle.solve(B, L)
+        assert util.rel_l2(dg.solution, x) <= util.TOL_SOLUTION, dg.solve_info
+
+
+def test_block_jacobi_still_available(rb):
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(2000, seed=2), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=2)
+    dg.add_data(**PROBLEMS["diffusion"]["data"])
+    dg.solver_options.update(preconditioner="bj", rtol=1e-8)
+    dg.dgfem(solve=True)
+    assert dg.solve_info["preconditioner"] == "bj" and dg.solve_info["converged"]
+    bj_its = dg.solve_info["iterations"]
+    dg.solver_options.update(preconditioner="mg")
+    dg.dgfem(solve=True)
+    assert dg.solve_info["iterations"] < bj_its

@@ -117,6 +117,11 @@ int reyna_b200_structure(const rb_geom *g, int has_diffusion, const uint8_t *if_
 int reyna_b200_csr_pattern(const rb_geom *g, const rb_structure *s, int p, int32_t *indptr, int32_t *indices,
                            void *stream);
 
+/* Same pattern with LOCAL column numbering (owned elements [0,n_rows), ghosts behind them): the matrix the distributed
+ * Krylov solver multiplies with (vector = owned coefficients followed by ghost coefficients). */
+int reyna_b200_csr_pattern_local(const rb_geom *g, const rb_structure *s, int p, int32_t *indptr, int32_t *indices,
+                                 void *stream);
+
 /* Volume + interior-face terms, summed per element in a fixed order and written straight into the CSR value array
  * (replaces DGFEM._stiffness_matrix + localstiff, main.py:275-327 / full_assembly.py:9-77, and
  * DGFEM._interior_stiffness_matrix + int_localstiff, main.py:329-374 / full_assembly.py:80-214).
@@ -194,6 +199,22 @@ int reyna_b200_solve(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d, i
                      const double *rhs, double *x, const rb_solve_opts *opts, rb_solve_info *info,
                      rb_halo_fn halo, rb_allreduce_fn allreduce, void *user, rb_mg *mg,
                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Multi-GPU solve (one process per GPU): NCCL halo exchange + all-reduce behind the rb_halo_fn / rb_allreduce_fn hooks.
+ * NCCL is resolved at run time (nccl_path, else the libnccl.so.2 already loaded by the process).  Rank 0 makes the
+ * 128-byte unique id and distributes it (e.g. torch.distributed.broadcast); every rank then creates its handle with the
+ * halo plan: peers, per-peer offsets (in elements) into the concatenated send list (device int32 of owned element ids)
+ * and into the ghost block (ghosts sorted by global id are contiguous per peer).  Pass reyna_b200_nccl_halo /
+ * reyna_b200_nccl_allreduce and the handle (as `user`) to reyna_b200_solve; x then has n_ghost extra entries. */
+typedef struct rb_dist rb_dist;
+int reyna_b200_nccl_unique_id(const char *nccl_path, char out[128]);
+int reyna_b200_dist_create(const char *nccl_path, const char id[128], int rank, int world, int d, int n_rows, int n_peers,
+                           const int *peer, const int *send_off, const int *recv_off, const int32_t *send_idx_dev,
+                           rb_dist **out);
+void reyna_b200_dist_destroy(rb_dist *h);
+int reyna_b200_dist_counters(const rb_dist *h, unsigned long long *exchanges, unsigned long long *allreduces);
+int reyna_b200_nccl_halo(void *user, double *x_dev, void *stream);
+int reyna_b200_nccl_allreduce(void *user, double *vals_dev, int n, void *stream);
 
 /* y = A x on the same matrix formats (exposed for tests and for the roofline measurement of the SpMV). */
 int reyna_b200_spmv(int32_t n_rows_scalar, int32_t d, int blocked, const int32_t *indptr, const int32_t *indices,

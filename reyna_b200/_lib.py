@@ -16,7 +16,9 @@ RB_MAX_QV = 16
 RB_MAX_QE = 4
 
 EXPORTS = (
-    "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_csr_pattern",
+    "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_csr_pattern", "reyna_b200_csr_pattern_local",
+    "reyna_b200_nccl_unique_id", "reyna_b200_dist_create", "reyna_b200_dist_destroy", "reyna_b200_dist_counters",
+    "reyna_b200_nccl_halo", "reyna_b200_nccl_allreduce",
     "reyna_b200_assemble_workspace", "reyna_b200_assemble",
     "reyna_b200_boundary", "reyna_b200_compact_workspace", "reyna_b200_compact_count", "reyna_b200_compact_fill",
     "reyna_b200_mg_create", "reyna_b200_mg_destroy", "reyna_b200_mg_info", "reyna_b200_mg_apply",
@@ -104,6 +106,17 @@ def lib() -> C.CDLL:
     L.reyna_b200_structure.argtypes = [C.POINTER(RbGeom), C.c_int, vp, C.POINTER(RbStructure), vp, C.c_size_t, vp]
     L.reyna_b200_csr_pattern.restype = C.c_int
     L.reyna_b200_csr_pattern.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.c_int, vp, vp, vp]
+    L.reyna_b200_csr_pattern_local.restype = C.c_int
+    L.reyna_b200_csr_pattern_local.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.c_int, vp, vp, vp]
+    L.reyna_b200_nccl_unique_id.restype = C.c_int
+    L.reyna_b200_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
+    L.reyna_b200_dist_create.restype = C.c_int
+    L.reyna_b200_dist_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.POINTER(vp)]
+    L.reyna_b200_dist_destroy.restype = None
+    L.reyna_b200_dist_destroy.argtypes = [vp]
+    L.reyna_b200_dist_counters.restype = C.c_int
+    L.reyna_b200_dist_counters.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.reyna_b200_assemble.restype = C.c_int
     L.reyna_b200_assemble.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.POINTER(RbCoefs), C.POINTER(RbQuad),
                                       C.c_double, vp, vp, i64p, vp, C.c_size_t, vp]

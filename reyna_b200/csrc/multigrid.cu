@@ -109,7 +109,11 @@ __global__ void mg_aggregate(int nc, int n, int agg, const int32_t* __restrict__
         int pos[8], end[8];
         const int r0 = I * agg;
         int nr = n - r0 < agg ? n - r0 : agg;
-        for (int k = 0; k < nr; ++k) { pos[k] = indptr[r0 + k]; end[k] = indptr[r0 + k + 1]; }
+        for (int k = 0; k < nr; ++k) {
+            pos[k] = indptr[r0 + k];
+            end[k] = indptr[r0 + k + 1];
+            while (end[k] > pos[k] && indices[end[k] - 1] >= n) --end[k];   // ghost columns (sorted last) are dropped
+        }
         int out = FILL ? c_cnt_or_indptr[I] : 0;
         int count = 0;
         for (;;) {
@@ -153,7 +157,8 @@ __global__ void __launch_bounds__(256) mg_dense_inverse(int n, const int32_t* __
     for (int i = tid; i < n * n; i += nt) { at[i] = 0.0; invt[i] = (i / n == i % n) ? 1.0 : 0.0; }
     __syncthreads();
     for (int r = tid; r < n; r += nt)
-        for (int k = indptr[r]; k < indptr[r + 1]; ++k) at[(size_t)indices[k] * n + r] = data[k];
+        for (int k = indptr[r]; k < indptr[r + 1]; ++k)
+            if (indices[k] < n) at[(size_t)indices[k] * n + r] = data[k];
     __syncthreads();
     for (int c = 0; c < n; ++c) {
         if (tid == 0) {
@@ -205,10 +210,14 @@ __global__ void mg_jacobi0(int n, double omega, const double* __restrict__ dinv,
 template <int G>
 __device__ __forceinline__ double row_dot(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                           const double* __restrict__ data, const double* __restrict__ x, int row, int lane,
-                                          unsigned gmask) {
+                                          unsigned gmask, int ncols) {
+    // columns >= ncols are ghost couplings of a partitioned matrix: the (rank-local) multigrid levels ignore them
     double s = 0.0;
     const int hi = indptr[row + 1];
-    for (int k = indptr[row] + lane; k < hi; k += G) s = fma(data[k], x[indices[k]], s);
+    for (int k = indptr[row] + lane; k < hi; k += G) {
+        const int c = indices[k];
+        if (c < ncols) s = fma(data[k], x[c], s);
+    }
 #pragma unroll
     for (int o = G / 2; o; o >>= 1) s += __shfl_xor_sync(gmask, s, o, G);
     return s;
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(kMgThreads) mg_jacobi(int n, double omega, con
     const unsigned gm = group_mask<G>();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += stride) {
-        const double ax = row_dot<G>(indptr, indices, data, x, (int)i, lane, gm);
+        const double ax = row_dot<G>(indptr, indices, data, x, (int)i, lane, gm, n);
         if (lane == 0) xo[i] = x[i] + omega * dinv[i] * (b[i] - ax);
     }
 }
@@ -247,7 +256,10 @@ __global__ void __launch_bounds__(kMgThreads) mg_restrict_residual(int nc, int n
         double s = 0.0;
         if (i < n) {
             const int hi = indptr[i + 1];
-            for (int k = indptr[i] + lane; k < hi; k += 4) s = fma(-data[k], x[indices[k]], s);
+            for (int k = indptr[i] + lane; k < hi; k += 4) {
+                const int c = indices[k];
+                if (c < n) s = fma(-data[k], x[c], s);
+            }
             if (lane == 0) s += b[i];
         }
         // fixed-shape tree over the 16 lanes: deterministic
@@ -296,7 +308,7 @@ __global__ void __launch_bounds__(kMgThreads) mg_residual(int n, const int32_t* 
     const unsigned gm = group_mask<G>();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += stride) {
-        const double ax = row_dot<G>(indptr, indices, data, x, (int)i, lane, gm);
+        const double ax = row_dot<G>(indptr, indices, data, x, (int)i, lane, gm, n);
         if (lane == 0) t[i] = b[i] - ax;
     }
 }

@@ -275,7 +275,9 @@ constexpr int kMaxNb = 64;   // neighbours per element held in shared memory (po
 
 // one warp per block row: every scalar row (e,j) of the block row has the same column list, so it is built once in
 // shared memory and streamed d times to the contiguous index range of the block row
+template <bool LOCAL>
 __global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows, int d, const int32_t* __restrict__ ielem,
+                                                                     const int32_t* __restrict__ adj_nb,
                                                                      const int32_t* __restrict__ gid,
                                                                      const int32_t* __restrict__ adj_off,
                                                                      const int32_t* __restrict__ adj_item,
@@ -297,22 +299,26 @@ __global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows,
         int below = 0;           // leaders with neighbour < e (= slot of the diagonal block)
         for (int a0 = lo; a0 < hi; a0 += 32) {
             const int a = a0 + lane;
-            int it = -1, o = -1;
+            int it = -1, o = -1, ol = -1;
             if (a < hi) {
                 it = adj_item[a];
-                if (it >= 0) o = gid_of(gid, ielem[2 * (it >> 1) + (1 - (it & 1))]);
+                if (it >= 0) {
+                    // neighbour id straight from the adjacency (no dependent load) when adj_sort recorded it
+                    ol = adj_nb ? adj_nb[a] : ielem[2 * (it >> 1) + (1 - (it & 1))];
+                    o = gid_of(gid, ol);
+                }
             }
             const bool leader = it >= 0;
             const unsigned m = __ballot_sync(0xffffffffu, leader);
             const unsigned mlow = __ballot_sync(0xffffffffu, leader && o < eg);
             if (leader) {
                 const int slot = before + __popc(m & ((1u << lane) - 1u)) + (o > eg ? 1 : 0);
-                if (slot <= kMaxNb) s_nb[w][slot] = o;
+                if (slot <= kMaxNb) s_nb[w][slot] = LOCAL ? ol : o;   // ordered by global id, numbered globally or locally
             }
             before += __popc(m);
             below += __popc(mlow);
         }
-        if (lane == 0 && below <= kMaxNb) s_nb[w][below] = eg;
+        if (lane == 0 && below <= kMaxNb) s_nb[w][below] = LOCAL ? e : eg;
         __syncwarp();
         const int64_t base = (int64_t)dd * (g0 + e);
         const int rowlen = nb * d;
@@ -380,9 +386,23 @@ extern "C" int reyna_b200_csr_pattern(const rb_geom* g, const rb_structure* s, i
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_csr_pattern: polynomial degree must be 1..3");
     const int d = (p + 1) * (p + 2) / 2;
     const int blocks = grid_for(g->n_rows, kPatWarps, kNumSMs * 8);
-    csr_pattern_kernel<<<blocks, kPatWarps * 32, 0, (cudaStream_t)stream>>>(g->n_rows, d, g->ielem, g->elem_gid, s->adj_off,
-                                                                              s->adj_item, s->grp_off, indptr, indices);
+    csr_pattern_kernel<false><<<blocks, kPatWarps * 32, 0, (cudaStream_t)stream>>>(g->n_rows, d, g->ielem, s->adj_nb, g->elem_gid,
+                                                                                     s->adj_off, s->adj_item, s->grp_off, indptr,
+                                                                                     indices);
     RB_LAUNCH_CHECK("csr_pattern_kernel");
+    return 0;
+}
+
+extern "C" int reyna_b200_csr_pattern_local(const rb_geom* g, const rb_structure* s, int p, int32_t* indptr,
+                                            int32_t* indices, void* stream) {
+    RB_REQUIRE(g && s && indptr && indices, RB_E_ARG, "reyna_b200_csr_pattern_local: null argument");
+    RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_csr_pattern_local: polynomial degree must be 1..3");
+    const int d = (p + 1) * (p + 2) / 2;
+    const int blocks = grid_for(g->n_rows, kPatWarps, kNumSMs * 8);
+    csr_pattern_kernel<true><<<blocks, kPatWarps * 32, 0, (cudaStream_t)stream>>>(g->n_rows, d, g->ielem, s->adj_nb, g->elem_gid,
+                                                                                    s->adj_off, s->adj_item, s->grp_off, indptr,
+                                                                                    indices);
+    RB_LAUNCH_CHECK("csr_pattern_kernel<local>");
     return 0;
 }
 

@@ -1,0 +1,200 @@
+"""Multi-GPU ``dgfem(solve=True)``: one process per GPU, elements partitioned into contiguous (Morton-ordered) ranges.
+
+The reference is a single-process program; this module is new.  Assembly needs no collective
+(``partition.py``).  The Krylov solve runs the same ``reyna_b200_solve`` on every rank with
+
+* the rank's block rows in LOCAL column numbering (owned coefficients followed by ghost coefficients),
+* a halo exchange of ghost-element coefficients before every SpMV and an all-reduce of every dot product, both issued
+  from inside the library over NCCL on the solver's stream (``csrc/dist.cu``),
+* the multigrid hierarchy built per rank on its own diagonal block (additive Schwarz across ranks, no coarse-level
+  communication).
+
+``torch.distributed`` (any backend) is only used to hand out the NCCL unique id and to gather the solution.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+import typing
+
+import numpy as np
+
+from . import _lib
+from .dgfem import DGFEM, _ptr
+from .geometry import flat_geometry
+from .partition import HaloPlan, PartitionedGeometry, partition_bounds, partition_geometry
+
+
+def nccl_library_path() -> typing.Optional[str]:
+    """The libnccl.so.2 that PyTorch loaded (so that exactly one NCCL lives in the process)."""
+    try:
+        import nvidia.nccl
+        for base in nvidia.nccl.__path__:
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+class DistributedDGFEM:
+    """``DGFEM`` on one rank's partition plus the distributed solve.
+
+    >>> ddg = DistributedDGFEM(geometry, polynomial_degree=2)        # inside a torch.distributed process group
+    >>> ddg.add_data(...); ddg.dgfem(solve=True)
+    >>> ddg.solution            # this rank's coefficients;  ddg.gather_solution() -> the global vector on every rank
+    """
+
+    def __init__(self, geometry, polynomial_degree: int = 1, rank: int = None, world: int = None, device=None):
+        import torch.distributed as dist
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.global_geometry = geometry
+        self.bounds = partition_bounds(int(geometry.n_elements), self.world)
+        self.part = partition_geometry(geometry, int(self.bounds[self.rank]), int(self.bounds[self.rank + 1]))
+        self.plan = HaloPlan(geometry, self.bounds, self.rank)
+        self.dg = DGFEM(self.part, polynomial_degree)
+        if device is not None:
+            self.dg.device = device
+        self.solution: typing.Optional[np.ndarray] = None
+        self.solve_info: typing.Optional[dict] = None
+        self._dist = None
+
+    # ---- pass-through of the reference API ------------------------------------------------------------------------------
+    def add_data(self, **kwargs):
+        self.dg.add_data(**kwargs)
+
+    @property
+    def solver_options(self):
+        return self.dg.solver_options
+
+    @property
+    def dim_elem(self):
+        return self.dg.dim_elem
+
+    def dgfem(self, solve: bool = True, verbose: int = 0):
+        self.dg.dgfem(solve=False, verbose=verbose)
+        if solve:
+            self.solution = self.solve()
+
+    # ---- NCCL context ---------------------------------------------------------------------------------------------------
+    def _context(self, torch, dev, d: int):
+        if self._dist is not None:
+            return self._dist
+        import torch.distributed as dist
+        L = _lib.lib()
+        path = nccl_library_path()
+        cpath = path.encode() if path else None
+        idbuf = C.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(L.reyna_b200_nccl_unique_id(cpath, idbuf), "reyna_b200_nccl_unique_id")
+        t = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device=dev if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, src=0)
+        idbytes = bytes(t.cpu().tolist())
+        peers = self.plan.peers()
+        send_idx, send_off, recv_off = [], [0], [0]
+        for q in peers:
+            s = self.plan.send.get(q, np.zeros(0, dtype=np.int64))
+            r = self.plan.recv.get(q, np.zeros(0, dtype=np.int64))
+            send_idx.append(np.asarray(s, dtype=np.int32))
+            send_off.append(send_off[-1] + len(s))
+            if len(r):
+                # ghosts of one peer are a contiguous block of the (gid-sorted) ghost layer
+                assert int(r[0]) - self.plan.n_rows == recv_off[-1] and np.all(np.diff(r) == 1)
+            recv_off.append(recv_off[-1] + len(r))
+        sidx = np.concatenate(send_idx) if send_idx else np.zeros(0, dtype=np.int32)
+        sidx_dev = torch.from_numpy(np.ascontiguousarray(sidx, dtype=np.int32)).to(dev) if sidx.size else \
+            torch.zeros(1, dtype=torch.int32, device=dev)
+        n = len(peers)
+        arr = lambda v: (C.c_int * max(1, len(v)))(*v)       # noqa: E731
+        handle = C.c_void_p(None)
+        _lib.check(L.reyna_b200_dist_create(cpath, idbytes, self.rank, self.world, d, self.plan.n_rows, n, arr(peers),
+                                            arr(send_off), arr(recv_off), sidx_dev.data_ptr(), C.byref(handle)),
+                   "reyna_b200_dist_create")
+        self._dist = dict(handle=handle, send_idx=sidx_dev)
+        return self._dist
+
+    def close(self):
+        if self._dist is not None:
+            _lib.lib().reyna_b200_dist_destroy(self._dist["handle"])
+            self._dist = None
+
+    # ---- solve ----------------------------------------------------------------------------------------------------------
+    def solve(self) -> np.ndarray:
+        torch = _lib.require_cuda()
+        L = _lib.lib()
+        dg = self.dg
+        dv = dg._dev
+        d, N = dv["d"], dv["n"]
+        fg = flat_geometry(self.part)
+        n_ghost = (fg.n_elem - fg.n_rows) * d
+        dev = dv["data"].device
+        so = dg.solver_options
+        method = so.get("method", "auto")
+        if method == "auto":
+            method = "cg" if dg.advection is None else "bicgstab"
+        prec = so.get("preconditioner", "auto")
+        if prec == "auto":
+            prec = "mg" if dg.diffusion is not None else "bj"
+        opts = _lib.RbSolveOpts(method=0 if method == "cg" else 1, max_iter=int(so.get("max_iter", 200000)),
+                                rtol=float(so.get("rtol", 1e-14)), check_every=int(so.get("check_every", 10)))
+        info = _lib.RbSolveInfo()
+        t0 = time.perf_counter()
+        with torch.cuda.device(dev):
+            sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            ctx = self._context(torch, dev, d)
+            # the rank's rows with local column numbering
+            g, st = dv["_assemble_call"][0], dv["_assemble_call"][1]
+            s_indptr, _, s_data = dv["structural"]
+            indices_local = torch.empty_like(dv["structural"][1])
+            indptr_local = torch.empty_like(s_indptr)
+            _lib.check(L.reyna_b200_csr_pattern_local(C.byref(g), C.byref(st), dg.polydegree, _ptr(indptr_local),
+                                                      _ptr(indices_local), sp), "reyna_b200_csr_pattern_local")
+            mg = C.c_void_p(None)
+            try:
+                if prec == "mg":
+                    mo = _lib.RbMgOpts(nu=int(so.get("mg_nu", 3)), omega=float(so.get("mg_omega", 0.7)),
+                                       alpha=float(so.get("mg_alpha", 1.8)))
+                    _lib.check(L.reyna_b200_mg_create(N, d, dg.polydegree, _ptr(indptr_local), _ptr(indices_local),
+                                                      _ptr(s_data), C.byref(mo), C.byref(mg), sp), "reyna_b200_mg_create")
+                x = torch.zeros(N + n_ghost, dtype=torch.float64, device=dev)
+                ws_bytes = L.reyna_b200_solve_workspace(N, n_ghost, d)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                halo = C.cast(L.reyna_b200_nccl_halo, C.c_void_p)
+                allr = C.cast(L.reyna_b200_nccl_allreduce, C.c_void_p)
+                _lib.check(L.reyna_b200_solve(N, n_ghost, d, 1, _ptr(indptr_local), _ptr(indices_local), _ptr(s_data),
+                                              _ptr(dv["load"]), _ptr(x), C.byref(opts), C.byref(info), halo, allr,
+                                              ctx["handle"], mg, _ptr(ws), ws_bytes, sp), "reyna_b200_solve")
+                sol = x[:N].cpu().numpy()
+            finally:
+                if mg.value:
+                    L.reyna_b200_mg_destroy(mg)
+        ex, ar = C.c_ulonglong(0), C.c_ulonglong(0)
+        L.reyna_b200_dist_counters(ctx["handle"], C.byref(ex), C.byref(ar))
+        self.solve_info = dict(method=method, preconditioner=prec, iterations=int(info.iterations),
+                               rel_residual=float(info.rel_residual), converged=bool(info.converged),
+                               restarts=int(info.restarts), stagnated=bool(info.stagnated), world=self.world,
+                               halo_exchanges=int(ex.value), allreduces=int(ar.value), n_ghost_elements=fg.n_elem - fg.n_rows,
+                               seconds=time.perf_counter() - t0)
+        return sol
+
+    def gather_solution(self) -> np.ndarray:
+        """The global coefficient vector (element order of the unpartitioned geometry) on every rank."""
+        import torch
+        import torch.distributed as dist
+        d = self.dg.dim_elem
+        sizes = [int(self.bounds[r + 1] - self.bounds[r]) * d for r in range(self.world)]
+        on_gpu = dist.get_backend() == "nccl"
+        dev = self.dg._dev["data"].device if on_gpu else "cpu"
+        mine = torch.from_numpy(np.ascontiguousarray(self.solution)).to(dev)
+        outs = [torch.empty(s, dtype=torch.float64, device=dev) for s in sizes]
+        dist.all_gather(outs, mine) if len(set(sizes)) == 1 else self._all_gather_uneven(dist, outs, mine)
+        return torch.cat(outs).cpu().numpy()
+
+    def _all_gather_uneven(self, dist, outs, mine):
+        for r in range(self.world):
+            if r == self.rank:
+                outs[r].copy_(mine)
+            dist.broadcast(outs[r], src=r)

@@ -185,8 +185,24 @@ typedef struct {
     double  omega;             /* Jacobi damping (default 0.7)                                                */
     double  alpha;             /* scaling of the aggregation coarse corrections (default 1.8)                 */
 } rb_mg_opts;
+/* Distributed hierarchy (dd != NULL): the fine and P1 levels are the rank's rows in LOCAL column numbering (halo exchange
+ * through dd->dist), the piecewise-constant level is GLOBAL: the caller gathers every rank's P0 rows (global element
+ * numbering) into one CSR matrix, which every rank coarsens and cycles redundantly -- the coarse space keeps its global
+ * reach, so iteration counts do not grow with the number of GPUs. */
+typedef struct rb_dist rb_dist;
+typedef struct {
+    rb_dist *dist;             /* NCCL context + halo plan (reyna_b200_dist_create)                          */
+    int32_t rank, world;
+    int32_t n_ghost_elem;      /* ghost elements behind the owned ones                                        */
+    int32_t n_global_elem;
+    const int32_t *bounds;     /* HOST [world+1]: rank r owns elements [bounds[r], bounds[r+1])               */
+    const int32_t *p0_indptr;  /* DEVICE [n_global_elem+1]   global P0 matrix                                 */
+    const int32_t *p0_indices; /* DEVICE [p0_nnz]            (global element ids, ascending per row)          */
+    const double  *p0_data;    /* DEVICE [p0_nnz]                                                             */
+    long long p0_nnz;
+} rb_mg_dist;
 int reyna_b200_mg_create(int32_t n_rows_scalar, int32_t d, int32_t p, const int32_t *indptr, const int32_t *indices,
-                         const double *data, const rb_mg_opts *opts, rb_mg **out, void *stream);
+                         const double *data, const rb_mg_opts *opts, const rb_mg_dist *dd, rb_mg **out, void *stream);
 void reyna_b200_mg_destroy(rb_mg *mg);
 int reyna_b200_mg_info(const rb_mg *mg, int32_t *n_levels, int32_t *level_rows /*[16]*/, long long *level_nnz /*[16]*/);
 /* z = coarse-space correction of r (the multigrid part of the preconditioner alone; exposed for tests) */
@@ -202,13 +218,15 @@ int reyna_b200_solve(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d, i
 
 /* Multi-GPU solve (one process per GPU): NCCL halo exchange + all-reduce behind the rb_halo_fn / rb_allreduce_fn hooks.
  * NCCL is resolved at run time (nccl_path, else the libnccl.so.2 already loaded by the process).  Rank 0 makes the
- * 128-byte unique id and distributes it (e.g. torch.distributed.broadcast); every rank then creates its handle with the
+ * 128-byte unique id and distributes it (e.g. torch.distributed.broadcast); every rank creates the communicator ONCE
+ * (reyna_b200_comm_create; seconds) and then, per partitioned system, a handle with the
  * halo plan: peers, per-peer offsets (in elements) into the concatenated send list (device int32 of owned element ids)
  * and into the ghost block (ghosts sorted by global id are contiguous per peer).  Pass reyna_b200_nccl_halo /
  * reyna_b200_nccl_allreduce and the handle (as `user`) to reyna_b200_solve; x then has n_ghost extra entries. */
-typedef struct rb_dist rb_dist;
 int reyna_b200_nccl_unique_id(const char *nccl_path, char out[128]);
-int reyna_b200_dist_create(const char *nccl_path, const char id[128], int rank, int world, int d, int n_rows, int n_peers,
+int reyna_b200_comm_create(const char *nccl_path, const char id[128], int rank, int world, void **comm_out);
+void reyna_b200_comm_destroy(void *comm);
+int reyna_b200_dist_create(void *comm, int rank, int world, int d, int n_rows, int n_peers,
                            const int *peer, const int *send_off, const int *recv_off, const int32_t *send_idx_dev,
                            rb_dist **out);
 void reyna_b200_dist_destroy(rb_dist *h);

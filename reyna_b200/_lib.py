@@ -17,7 +17,7 @@ RB_MAX_QE = 4
 
 EXPORTS = (
     "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_csr_pattern", "reyna_b200_csr_pattern_local",
-    "reyna_b200_nccl_unique_id", "reyna_b200_dist_create", "reyna_b200_dist_destroy", "reyna_b200_dist_counters",
+    "reyna_b200_nccl_unique_id", "reyna_b200_comm_create", "reyna_b200_comm_destroy", "reyna_b200_dist_create", "reyna_b200_dist_destroy", "reyna_b200_dist_counters",
     "reyna_b200_nccl_halo", "reyna_b200_nccl_allreduce",
     "reyna_b200_assemble_workspace", "reyna_b200_assemble",
     "reyna_b200_boundary", "reyna_b200_compact_workspace", "reyna_b200_compact_count", "reyna_b200_compact_fill",
@@ -56,6 +56,12 @@ class RbStructure(C.Structure):
 
 class RbMgOpts(C.Structure):
     _fields_ = [("nu", C.c_int32), ("omega", C.c_double), ("alpha", C.c_double)]
+
+
+class RbMgDist(C.Structure):
+    _fields_ = [("dist", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("n_ghost_elem", C.c_int32),
+                ("n_global_elem", C.c_int32), ("bounds", C.c_void_p), ("p0_indptr", C.c_void_p), ("p0_indices", C.c_void_p),
+                ("p0_data", C.c_void_p), ("p0_nnz", C.c_longlong)]
 
 
 class RbSolveOpts(C.Structure):
@@ -111,8 +117,12 @@ def lib() -> C.CDLL:
     L.reyna_b200_nccl_unique_id.restype = C.c_int
     L.reyna_b200_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
     L.reyna_b200_dist_create.restype = C.c_int
-    L.reyna_b200_dist_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    L.reyna_b200_dist_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.POINTER(vp)]
+    L.reyna_b200_comm_create.restype = C.c_int
+    L.reyna_b200_comm_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    L.reyna_b200_comm_destroy.restype = None
+    L.reyna_b200_comm_destroy.argtypes = [vp]
     L.reyna_b200_dist_destroy.restype = None
     L.reyna_b200_dist_destroy.argtypes = [vp]
     L.reyna_b200_dist_counters.restype = C.c_int
@@ -137,7 +147,7 @@ def lib() -> C.CDLL:
     L.reyna_b200_solve.argtypes = [i32, i32, i32, C.c_int, vp, vp, vp, vp, vp, C.POINTER(RbSolveOpts),
                                    C.POINTER(RbSolveInfo), vp, vp, vp, vp, vp, C.c_size_t, vp]
     L.reyna_b200_mg_create.restype = C.c_int
-    L.reyna_b200_mg_create.argtypes = [i32, i32, i32, vp, vp, vp, C.POINTER(RbMgOpts), C.POINTER(vp), vp]
+    L.reyna_b200_mg_create.argtypes = [i32, i32, i32, vp, vp, vp, C.POINTER(RbMgOpts), C.POINTER(RbMgDist), C.POINTER(vp), vp]
     L.reyna_b200_mg_destroy.restype = None
     L.reyna_b200_mg_destroy.argtypes = [vp]
     L.reyna_b200_mg_info.restype = C.c_int

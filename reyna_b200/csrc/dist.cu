@@ -26,6 +26,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -51,6 +52,7 @@ static int load_nccl(const char* path) {
     RB_SYM(Send, "ncclSend")
     RB_SYM(Recv, "ncclRecv")
     RB_SYM(AllReduce, "ncclAllReduce")
+    RB_SYM(Broadcast, "ncclBroadcast")
     RB_SYM(GetErrorString, "ncclGetErrorString")
 #undef RB_SYM
     g_nccl = a;
@@ -98,15 +100,32 @@ extern "C" int reyna_b200_nccl_unique_id(const char* nccl_path, char out[128]) {
     return 0;
 }
 
-// plan arrays are HOST arrays except send_idx (device); offsets are in elements; ghosts received from peer[i] occupy the
-// ghost block [recv_off[i], recv_off[i+1]) (ghosts are sorted by global id, peers own contiguous id ranges).
-extern "C" int reyna_b200_dist_create(const char* nccl_path, const char id[128], int rank, int world, int d, int n_rows,
-                                      int n_peers, const int* peer, const int* send_off, const int* recv_off,
-                                      const int32_t* send_idx_dev, rb_dist** out) {
-    RB_REQUIRE(id && out && n_peers >= 0 && n_peers <= 64, RB_E_ARG, "reyna_b200_dist_create: bad argument");
+// One NCCL communicator per process and world (creation costs 0.3 ... several seconds): created once, shared by every
+// halo plan / solve.
+extern "C" int reyna_b200_comm_create(const char* nccl_path, const char id[128], int rank, int world, void** comm_out) {
+    RB_REQUIRE(id && comm_out, RB_E_ARG, "reyna_b200_comm_create: bad argument");
     int rc = load_nccl(nccl_path);
     if (rc) return rc;
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    ncclComm_t comm = nullptr;
+    RB_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
+    *comm_out = (void*)comm;
+    return 0;
+}
+
+extern "C" void reyna_b200_comm_destroy(void* comm) {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)comm);
+}
+
+// plan arrays are HOST arrays except send_idx (device); offsets are in elements; ghosts received from peer[i] occupy the
+// ghost block [recv_off[i], recv_off[i+1]) (ghosts are sorted by global id, peers own contiguous id ranges).
+extern "C" int reyna_b200_dist_create(void* comm, int rank, int world, int d, int n_rows, int n_peers, const int* peer,
+                                      const int* send_off, const int* recv_off, const int32_t* send_idx_dev,
+                                      rb_dist** out) {
+    RB_REQUIRE(comm && out && n_peers >= 0 && n_peers <= 64, RB_E_ARG, "reyna_b200_dist_create: bad argument");
     rb_dist* h = new rb_dist();
+    h->comm = (ncclComm_t)comm;
     h->rank = rank; h->world = world; h->d = d; h->n_rows = n_rows; h->n_peers = n_peers;
     for (int i = 0; i < n_peers; ++i) h->peer[i] = peer[i];
     for (int i = 0; i <= n_peers; ++i) { h->send_off[i] = send_off[i]; h->recv_off[i] = recv_off[i]; }
@@ -117,22 +136,12 @@ extern "C" int reyna_b200_dist_create(const char* nccl_path, const char id[128],
         delete h;
         return RB_E_WORKSPACE;
     }
-    ncclUniqueId uid;
-    memcpy(uid.internal, id, 128);
-    ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, uid, rank);
-    if (r != 0) {
-        set_error("ncclCommInitRank: %s", g_nccl.GetErrorString(r));
-        cudaFree(h->pack);
-        delete h;
-        return 1000 + r;
-    }
     *out = h;
     return 0;
 }
 
 extern "C" void reyna_b200_dist_destroy(rb_dist* h) {
     if (!h) return;
-    if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->pack) cudaFree(h->pack);
     delete h;
 }
@@ -144,12 +153,11 @@ extern "C" int reyna_b200_dist_counters(const rb_dist* h, unsigned long long* ex
     return 0;
 }
 
-// rb_halo_fn: refresh the ghost block of x (owned part [0, n_rows*d), ghosts behind it) -- one grouped send/recv
-extern "C" int reyna_b200_nccl_halo(void* user, double* x, void* stream) {
-    rb_dist* h = (rb_dist*)user;
+namespace rb {
+
+// refresh the ghost block of x holding `d` coefficients per element (d <= the handle's d) -- one grouped send/recv
+int dist_halo_d(rb_dist* h, double* x, int d, cudaStream_t st) {
     if (!h || h->n_peers == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int d = h->d;
     const int n_send = h->send_off[h->n_peers];
     if (n_send > 0) {
         halo_pack<<<grid_for((int64_t)n_send * d, 256, kNumSMs * 4), 256, 0, st>>>(n_send, d, h->send_idx, x, h->pack);
@@ -165,6 +173,33 @@ extern "C" int reyna_b200_nccl_halo(void* user, double* x, void* stream) {
     RB_NCCL(g_nccl.GroupEnd());
     ++h->exchanges;
     return 0;
+}
+
+// all ranks obtain the concatenation of every rank's `local` slice (rank r contributes global[bounds[r] .. bounds[r+1]))
+int dist_allgather_rows(rb_dist* h, const double* local, double* global, const int32_t* bounds, cudaStream_t st) {
+    if (!h) return RB_E_ARG;
+    RB_NCCL(g_nccl.GroupStart());
+    for (int r = 0; r < h->world; ++r) {
+        const size_t cnt = (size_t)(bounds[r + 1] - bounds[r]);
+        if (cnt == 0) continue;
+        RB_NCCL(g_nccl.Broadcast(r == h->rank ? (const void*)local : (const void*)(global + bounds[r]), global + bounds[r], cnt,
+                                 ncclFloat64, r, h->comm, st));
+    }
+    RB_NCCL(g_nccl.GroupEnd());
+    ++h->allreduces;
+    return 0;
+}
+
+int dist_rank(const rb_dist* h) { return h ? h->rank : 0; }
+int dist_world(const rb_dist* h) { return h ? h->world : 1; }
+
+}  // namespace rb
+
+// rb_halo_fn: refresh the ghost block of x (owned part [0, n_rows*d), ghosts behind it)
+extern "C" int reyna_b200_nccl_halo(void* user, double* x, void* stream) {
+    rb_dist* h = (rb_dist*)user;
+    if (!h) return 0;
+    return dist_halo_d(h, x, h->d, (cudaStream_t)stream);
 }
 
 // rb_allreduce_fn: in-place sum of n doubles over all ranks

@@ -36,6 +36,8 @@ struct MgLevel {
 
 }  // namespace rb
 
+struct rb_dist;
+
 struct rb_mg {
     int n_f = 0, d = 0, p = 0, n_elem = 0;
     const int32_t *f_indptr = nullptr, *f_indices = nullptr;
@@ -44,6 +46,7 @@ struct rb_mg {
     int has_p1 = 0;
     int32_t *p1_indptr = nullptr, *p1_indices = nullptr;
     double *p1_data = nullptr, *p1_minv = nullptr, *p1_r = nullptr, *p1_x = nullptr, *p1_t = nullptr;
+    double* p1_t0 = nullptr;       // distributed mode: this rank's P0 right-hand side before the all-gather
     int sel1[3] = {0, 1, 2};
     // P0 chain
     int nlev = 0;
@@ -51,6 +54,10 @@ struct rb_mg {
     double* dense_inv = nullptr;
     int nu = 3;
     double omega = 0.7, alpha = 1.8;
+    // distributed mode: fine and P1 levels are partitioned (halo exchange), the P0 chain is global and replicated
+    rb_dist* dist = nullptr;
+    int n_ghost_elem = 0, lo_elem = 0;
+    std::vector<int32_t> bounds;
     std::vector<void*> owned;
 };
 
@@ -109,10 +116,12 @@ __global__ void mg_aggregate(int nc, int n, int agg, const int32_t* __restrict__
         int pos[8], end[8];
         const int r0 = I * agg;
         int nr = n - r0 < agg ? n - r0 : agg;
+        // Ghost columns (>= n; a partitioned matrix orders its blocks by GLOBAL element id, so they can sit anywhere in a row)
+        // are skipped; the remaining owned columns are ascending.
         for (int k = 0; k < nr; ++k) {
             pos[k] = indptr[r0 + k];
             end[k] = indptr[r0 + k + 1];
-            while (end[k] > pos[k] && indices[end[k] - 1] >= n) --end[k];   // ghost columns (sorted last) are dropped
+            while (pos[k] < end[k] && indices[pos[k]] >= n) ++pos[k];
         }
         int out = FILL ? c_cnt_or_indptr[I] : 0;
         int count = 0;
@@ -122,8 +131,13 @@ __global__ void mg_aggregate(int nc, int n, int agg, const int32_t* __restrict__
                 if (pos[k] < end[k]) { const int c = indices[pos[k]] / agg; cmin = c < cmin ? c : cmin; }
             if (cmin == 0x7fffffff) break;
             double v = 0.0;
-            for (int k = 0; k < nr; ++k)          // fixed order: rows ascending, entries ascending -> deterministic
-                while (pos[k] < end[k] && indices[pos[k]] / agg == cmin) { if (FILL) v += data[pos[k]]; ++pos[k]; }
+            for (int k = 0; k < nr; ++k) {        // fixed order: rows ascending, entries ascending -> deterministic
+                while (pos[k] < end[k] && indices[pos[k]] / agg == cmin) {
+                    if (FILL) v += data[pos[k]];
+                    ++pos[k];
+                    while (pos[k] < end[k] && indices[pos[k]] >= n) ++pos[k];
+                }
+            }
             if (FILL) {
                 c_indices[out] = cmin;
                 c_data[out] = v;
@@ -230,7 +244,7 @@ __device__ __forceinline__ unsigned group_mask() {
 
 // xo = x + omega * dinv * (b - A x)
 template <int G>
-__global__ void __launch_bounds__(kMgThreads) mg_jacobi(int n, double omega, const int32_t* __restrict__ indptr,
+__global__ void __launch_bounds__(kMgThreads) mg_jacobi(int n, int ncols, double omega, const int32_t* __restrict__ indptr,
                                                         const int32_t* __restrict__ indices, const double* __restrict__ data,
                                                         const double* __restrict__ dinv, const double* __restrict__ b,
                                                         const double* __restrict__ x, double* __restrict__ xo) {
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(kMgThreads) mg_jacobi(int n, double omega, con
     const unsigned gm = group_mask<G>();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += stride) {
-        const double ax = row_dot<G>(indptr, indices, data, x, (int)i, lane, gm, n);
+        const double ax = row_dot<G>(indptr, indices, data, x, (int)i, lane, gm, ncols);
         if (lane == 0) xo[i] = x[i] + omega * dinv[i] * (b[i] - ax);
     }
 }
@@ -300,7 +314,7 @@ __global__ void mg_block_apply(int n, int dc, const double* __restrict__ minv, c
 
 // t = b - A x
 template <int G>
-__global__ void __launch_bounds__(kMgThreads) mg_residual(int n, const int32_t* __restrict__ indptr,
+__global__ void __launch_bounds__(kMgThreads) mg_residual(int n, int ncols, const int32_t* __restrict__ indptr,
                                                           const int32_t* __restrict__ indices, const double* __restrict__ data,
                                                           const double* __restrict__ b, const double* __restrict__ x,
                                                           double* __restrict__ t) {
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(kMgThreads) mg_residual(int n, const int32_t* 
     const unsigned gm = group_mask<G>();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += stride) {
-        const double ax = row_dot<G>(indptr, indices, data, x, (int)i, lane, gm, n);
+        const double ax = row_dot<G>(indptr, indices, data, x, (int)i, lane, gm, ncols);
         if (lane == 0) t[i] = b[i] - ax;
     }
 }
@@ -350,7 +364,7 @@ static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     double *x = L.x, *xt = L.xt;
     mg_jacobi0<<<g, kMgThreads, 0, st>>>(L.n, mg->omega, L.dinv, L.b, x);
     for (int s = 1; s < mg->nu; ++s) {
-        mg_jacobi<4><<<mg_grid((int64_t)L.n * 4), kMgThreads, 0, st>>>(L.n, mg->omega, L.indptr, L.indices, L.data, L.dinv, L.b, x, xt);
+        mg_jacobi<4><<<mg_grid((int64_t)L.n * 4), kMgThreads, 0, st>>>(L.n, L.n, mg->omega, L.indptr, L.indices, L.data, L.dinv, L.b, x, xt);
         double* t = x; x = xt; xt = t;
     }
     RB_LAUNCH_CHECK("mg_jacobi (pre)");
@@ -361,7 +375,7 @@ static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     if (rc) return rc;
     mg_prolong_add<<<g, kMgThreads, 0, st>>>(L.n, 4, mg->alpha, C.x, x);
     for (int s = 0; s < mg->nu; ++s) {
-        mg_jacobi<4><<<mg_grid((int64_t)L.n * 4), kMgThreads, 0, st>>>(L.n, mg->omega, L.indptr, L.indices, L.data, L.dinv, L.b, x, xt);
+        mg_jacobi<4><<<mg_grid((int64_t)L.n * 4), kMgThreads, 0, st>>>(L.n, L.n, mg->omega, L.indptr, L.indices, L.data, L.dinv, L.b, x, xt);
         double* t = x; x = xt; xt = t;
     }
     RB_LAUNCH_CHECK("mg_jacobi (post)");
@@ -371,31 +385,62 @@ static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     return 0;
 }
 
-// z += (coarse-space correction of r); r, z fine-level vectors
+int dist_halo_d(rb_dist* h, double* x, int d, cudaStream_t st);                                           // dist.cu
+int dist_allgather_rows(rb_dist* h, const double* local, double* global, const int32_t* bounds, cudaStream_t st);
+
+// out[i] = in[offset + i]
+__global__ void mg_copy_slice(int n, const double* __restrict__ in, int offset, double* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[offset + i];
+}
+
+// P0 correction of the element-wise right-hand side `b0_local` (this rank's elements) -> x0_local.  Single GPU: the chain
+// is local.  Distributed: the right-hand side is all-gathered, every rank runs the (small, global) chain redundantly and
+// keeps its slice -- the coarse space stays GLOBAL, so iteration counts do not depend on the number of GPUs.
+static int mg_p0_correction(rb_mg* mg, cudaStream_t st) {
+    return mg_vcycle(mg, 0, st);
+}
+
+// z += (coarse-space correction of r); r, z fine-level vectors (owned part)
 int mg_apply_add(rb_mg* mg, const double* r, double* z, cudaStream_t st) {
     const int E = mg->n_elem, d = mg->d;
     MgLevel& L0 = mg->lev[0];
+    const bool dist = mg->dist != nullptr;
+    // in distributed mode the local P0 right-hand side / correction live in the ping-pong vector of level 0's tail
+    double* b0_local = dist ? mg->p1_t0 : L0.b;
+    int rc;
     if (mg->has_p1) {
         const int n1 = 3 * E, g1 = mg_grid(n1);
+        const int nc1 = 3 * (E + mg->n_ghost_elem);
         const int s0 = mg->sel1[0], s1 = mg->sel1[1], s2 = mg->sel1[2];
         mg_select<<<g1, kMgThreads, 0, st>>>(E, d, 3, s0, s1, s2, r, mg->p1_r);
         mg_block_apply<false><<<g1, kMgThreads, 0, st>>>(n1, 3, mg->p1_minv, mg->p1_r, mg->p1_x);          // pre-smoothing
-        mg_residual<8><<<mg_grid((int64_t)n1 * 8), kMgThreads, 0, st>>>(n1, mg->p1_indptr, mg->p1_indices, mg->p1_data, mg->p1_r, mg->p1_x, mg->p1_t);
-        mg_select<<<mg_grid(E), kMgThreads, 0, st>>>(E, 3, 1, 0, 0, 0, mg->p1_t, L0.b);
+        RB_LAUNCH_CHECK("mg p1 pre");
+        if (dist && (rc = dist_halo_d(mg->dist, mg->p1_x, 3, st))) return rc;
+        mg_residual<8><<<mg_grid((int64_t)n1 * 8), kMgThreads, 0, st>>>(n1, nc1, mg->p1_indptr, mg->p1_indices, mg->p1_data,
+                                                                       mg->p1_r, mg->p1_x, mg->p1_t);
+        mg_select<<<mg_grid(E), kMgThreads, 0, st>>>(E, 3, 1, 0, 0, 0, mg->p1_t, b0_local);
         RB_LAUNCH_CHECK("mg p1 down");
-        int rc = mg_vcycle(mg, 0, st);
-        if (rc) return rc;
-        mg_pad_add<<<mg_grid(E), kMgThreads, 0, st>>>(E, 3, 1, 0, 0, 0, L0.x, mg->p1_x);
-        mg_residual<8><<<mg_grid((int64_t)n1 * 8), kMgThreads, 0, st>>>(n1, mg->p1_indptr, mg->p1_indices, mg->p1_data, mg->p1_r, mg->p1_x, mg->p1_t);
+    } else {
+        mg_select<<<mg_grid(E), kMgThreads, 0, st>>>(E, d, 1, 0, 0, 0, r, b0_local);
+        RB_LAUNCH_CHECK("mg_select");
+    }
+    if (dist && (rc = dist_allgather_rows(mg->dist, b0_local, L0.b, mg->bounds.data(), st))) return rc;
+    if ((rc = mg_p0_correction(mg, st))) return rc;
+    const double* x0_local = L0.x + (dist ? mg->lo_elem : 0);
+    if (mg->has_p1) {
+        const int n1 = 3 * E, g1 = mg_grid(n1);
+        const int nc1 = 3 * (E + mg->n_ghost_elem);
+        const int s0 = mg->sel1[0], s1 = mg->sel1[1], s2 = mg->sel1[2];
+        mg_pad_add<<<mg_grid(E), kMgThreads, 0, st>>>(E, 3, 1, 0, 0, 0, x0_local, mg->p1_x);
+        RB_LAUNCH_CHECK("mg_pad_add");
+        if (dist && (rc = dist_halo_d(mg->dist, mg->p1_x, 3, st))) return rc;
+        mg_residual<8><<<mg_grid((int64_t)n1 * 8), kMgThreads, 0, st>>>(n1, nc1, mg->p1_indptr, mg->p1_indices, mg->p1_data,
+                                                                       mg->p1_r, mg->p1_x, mg->p1_t);
         mg_block_apply<true><<<g1, kMgThreads, 0, st>>>(n1, 3, mg->p1_minv, mg->p1_t, mg->p1_x);           // post-smoothing
         mg_pad_add<<<g1, kMgThreads, 0, st>>>(E, d, 3, s0, s1, s2, mg->p1_x, z);
         RB_LAUNCH_CHECK("mg p1 up");
     } else {
-        mg_select<<<mg_grid(E), kMgThreads, 0, st>>>(E, d, 1, 0, 0, 0, r, L0.b);
-        RB_LAUNCH_CHECK("mg_select");
-        int rc = mg_vcycle(mg, 0, st);
-        if (rc) return rc;
-        mg_pad_add<<<mg_grid(E), kMgThreads, 0, st>>>(E, d, 1, 0, 0, 0, L0.x, z);
+        mg_pad_add<<<mg_grid(E), kMgThreads, 0, st>>>(E, d, 1, 0, 0, 0, x0_local, z);
         RB_LAUNCH_CHECK("mg_pad_add");
     }
     return 0;
@@ -412,7 +457,8 @@ extern "C" void reyna_b200_mg_destroy(rb_mg* mg) {
 }
 
 extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32_t* indptr, const int32_t* indices,
-                                    const double* data, const rb_mg_opts* opts, rb_mg** out, void* stream) {
+                                    const double* data, const rb_mg_opts* opts, const rb_mg_dist* dd, rb_mg** out,
+                                    void* stream) {
     RB_REQUIRE(indptr && indices && data && out, RB_E_ARG, "reyna_b200_mg_create: null argument");
     RB_REQUIRE(d >= 1 && n % d == 0 && d == (p + 1) * (p + 2) / 2, RB_E_ARG, "reyna_b200_mg_create: bad block size");
     cudaStream_t st = (cudaStream_t)stream;
@@ -427,6 +473,16 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
     const int E = mg->n_elem;
     int rc = 0;
     auto fail = [&](int code) { reyna_b200_mg_destroy(mg); return code; };
+    if (dd) {
+        if (!dd->dist || !dd->bounds || !dd->p0_indptr || !dd->p0_indices || !dd->p0_data) {
+            set_error("reyna_b200_mg_create: incomplete rb_mg_dist");
+            return fail(RB_E_ARG);
+        }
+        mg->dist = dd->dist;
+        mg->n_ghost_elem = dd->n_ghost_elem;
+        mg->bounds.assign(dd->bounds, dd->bounds + dd->world + 1);
+        mg->lo_elem = dd->bounds[dd->rank];
+    }
     int32_t h_last = 0;
     RB_CUDA(cudaMemcpyAsync(&h_last, indptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
@@ -435,11 +491,21 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
 
     // ---- P1 level --------------------------------------------------------------------------------------------------
     MgLevel& L0 = mg->lev[0];
-    L0.n = E;
-    L0.nnz = nblocks;
-    if ((rc = dev_alloc(mg, (void**)&L0.indptr, sizeof(int32_t) * ((size_t)E + 1)))) return fail(rc);
-    if ((rc = dev_alloc(mg, (void**)&L0.indices, sizeof(int32_t) * (size_t)nblocks))) return fail(rc);
-    if ((rc = dev_alloc(mg, (void**)&L0.data, sizeof(double) * (size_t)nblocks))) return fail(rc);
+    if (dd) {
+        // the GLOBAL piecewise-constant matrix (all ranks' rows, gathered by the caller), replicated on every rank
+        L0.n = dd->n_global_elem;
+        L0.nnz = dd->p0_nnz;
+        L0.indptr = const_cast<int32_t*>(dd->p0_indptr);
+        L0.indices = const_cast<int32_t*>(dd->p0_indices);
+        L0.data = const_cast<double*>(dd->p0_data);
+        if ((rc = dev_alloc(mg, (void**)&mg->p1_t0, sizeof(double) * (size_t)E))) return fail(rc);
+    } else {
+        L0.n = E;
+        L0.nnz = nblocks;
+        if ((rc = dev_alloc(mg, (void**)&L0.indptr, sizeof(int32_t) * ((size_t)E + 1)))) return fail(rc);
+        if ((rc = dev_alloc(mg, (void**)&L0.indices, sizeof(int32_t) * (size_t)nblocks))) return fail(rc);
+        if ((rc = dev_alloc(mg, (void**)&L0.data, sizeof(double) * (size_t)nblocks))) return fail(rc);
+    }
     if (d > 3) {
         mg->has_p1 = 1;
         mg->sel1[0] = 0; mg->sel1[1] = 1; mg->sel1[2] = p + 1;     // modes (0,0), (0,1), (1,0) in Basis_index2D order
@@ -449,7 +515,8 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
         if ((rc = dev_alloc(mg, (void**)&mg->p1_data, sizeof(double) * (size_t)nblocks * 9))) return fail(rc);
         if ((rc = dev_alloc(mg, (void**)&mg->p1_minv, sizeof(double) * (size_t)n1 * 3))) return fail(rc);
         if ((rc = dev_alloc(mg, (void**)&mg->p1_r, sizeof(double) * (size_t)n1))) return fail(rc);
-        if ((rc = dev_alloc(mg, (void**)&mg->p1_x, sizeof(double) * (size_t)n1))) return fail(rc);
+        if ((rc = dev_alloc(mg, (void**)&mg->p1_x, sizeof(double) * ((size_t)n1 + 3 * (size_t)mg->n_ghost_elem)))) return fail(rc);
+        RB_CUDA(cudaMemsetAsync(mg->p1_x, 0, sizeof(double) * ((size_t)n1 + 3 * (size_t)mg->n_ghost_elem), st));
         if ((rc = dev_alloc(mg, (void**)&mg->p1_t, sizeof(double) * (size_t)n1))) return fail(rc);
         mg_extract_modes<<<mg_grid(n1), kMgThreads, 0, st>>>(E, d, 3, mg->sel1[0], mg->sel1[1], mg->sel1[2], indptr, indices,
                                                             data, mg->p1_indptr, mg->p1_indices, mg->p1_data);
@@ -457,9 +524,10 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
         if ((rc = dev_alloc(mg, (void**)&sing, sizeof(int)))) return fail(rc);
         cudaMemsetAsync(sing, 0, sizeof(int), st);
         block_jacobi_setup_launch(E, 3, mg->p1_indptr, mg->p1_indices, mg->p1_data, mg->p1_minv, sing, st);
-        mg_extract_modes<<<mg_grid(E), kMgThreads, 0, st>>>(E, 3, 1, 0, 0, 0, mg->p1_indptr, mg->p1_indices, mg->p1_data,
-                                                           L0.indptr, L0.indices, L0.data);
-    } else {
+        if (!dd)
+            mg_extract_modes<<<mg_grid(E), kMgThreads, 0, st>>>(E, 3, 1, 0, 0, 0, mg->p1_indptr, mg->p1_indices, mg->p1_data,
+                                                               L0.indptr, L0.indices, L0.data);
+    } else if (!dd) {
         mg_extract_modes<<<mg_grid(E), kMgThreads, 0, st>>>(E, d, 1, 0, 0, 0, indptr, indices, data, L0.indptr, L0.indices,
                                                            L0.data);
     }
@@ -477,7 +545,7 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
     if ((rc = alloc_vectors(L0))) return fail(rc);
     mg_diag_inv<<<mg_grid(L0.n), kMgThreads, 0, st>>>(L0.n, L0.indptr, L0.indices, L0.data, L0.dinv);
     int32_t* scratch = nullptr;
-    if ((rc = dev_alloc(mg, (void**)&scratch, sizeof(int32_t) * (scan_scratch_ints((int64_t)E + 1) + 4)))) return fail(rc);
+    if ((rc = dev_alloc(mg, (void**)&scratch, sizeof(int32_t) * (scan_scratch_ints((int64_t)L0.n + 1) + 4)))) return fail(rc);
     int k = 0;
     while (mg->lev[k].n > kDenseMax && k < kMaxLevels - 1) {
         MgLevel& L = mg->lev[k];

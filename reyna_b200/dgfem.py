@@ -439,7 +439,7 @@ class DGFEM:
                     mo = _lib.RbMgOpts(nu=int(so.get('mg_nu', 3)), omega=float(so.get('mg_omega', 0.7)),
                                        alpha=float(so.get('mg_alpha', 1.8)))
                     _lib.check(L.reyna_b200_mg_create(N, d, self.polydegree, _ptr(s_indptr), _ptr(s_indices), _ptr(s_data),
-                                                      C.byref(mo), C.byref(mg), sp), 'reyna_b200_mg_create')
+                                                      C.byref(mo), None, C.byref(mg), sp), 'reyna_b200_mg_create')
                     nl = C.c_int32(0)
                     rows = (C.c_int32 * 16)()
                     L.reyna_b200_mg_info(mg, C.byref(nl), rows, None)

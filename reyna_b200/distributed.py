@@ -39,6 +39,29 @@ def nccl_library_path() -> typing.Optional[str]:
     return None
 
 
+_COMM = {}
+
+
+def _communicator(torch, dev, rank: int, world: int):
+    """The process's NCCL communicator for this world (created once: ncclCommInitRank takes 0.3 ... several seconds)."""
+    key = (world, rank, str(dev))
+    if key in _COMM:
+        return _COMM[key]
+    import torch.distributed as dist
+    L = _lib.lib()
+    path = nccl_library_path()
+    cpath = path.encode() if path else None
+    idbuf = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(L.reyna_b200_nccl_unique_id(cpath, idbuf), "reyna_b200_nccl_unique_id")
+    t = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device=dev if dist.get_backend() == "nccl" else "cpu")
+    dist.broadcast(t, src=0)
+    comm = C.c_void_p(None)
+    _lib.check(L.reyna_b200_comm_create(cpath, bytes(t.cpu().tolist()), rank, world, C.byref(comm)), "reyna_b200_comm_create")
+    _COMM[key] = comm
+    return comm
+
+
 class DistributedDGFEM:
     """``DGFEM`` on one rank's partition plus the distributed solve.
 
@@ -83,16 +106,8 @@ class DistributedDGFEM:
     def _context(self, torch, dev, d: int):
         if self._dist is not None:
             return self._dist
-        import torch.distributed as dist
         L = _lib.lib()
-        path = nccl_library_path()
-        cpath = path.encode() if path else None
-        idbuf = C.create_string_buffer(128)
-        if self.rank == 0:
-            _lib.check(L.reyna_b200_nccl_unique_id(cpath, idbuf), "reyna_b200_nccl_unique_id")
-        t = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device=dev if dist.get_backend() == "nccl" else "cpu")
-        dist.broadcast(t, src=0)
-        idbytes = bytes(t.cpu().tolist())
+        comm = _communicator(torch, dev, self.rank, self.world)
         peers = self.plan.peers()
         send_idx, send_off, recv_off = [], [0], [0]
         for q in peers:
@@ -110,7 +125,7 @@ class DistributedDGFEM:
         n = len(peers)
         arr = lambda v: (C.c_int * max(1, len(v)))(*v)       # noqa: E731
         handle = C.c_void_p(None)
-        _lib.check(L.reyna_b200_dist_create(cpath, idbytes, self.rank, self.world, d, self.plan.n_rows, n, arr(peers),
+        _lib.check(L.reyna_b200_dist_create(comm, self.rank, self.world, d, self.plan.n_rows, n, arr(peers),
                                             arr(send_off), arr(recv_off), sidx_dev.data_ptr(), C.byref(handle)),
                    "reyna_b200_dist_create")
         self._dist = dict(handle=handle, send_idx=sidx_dev)
@@ -145,6 +160,7 @@ class DistributedDGFEM:
         with torch.cuda.device(dev):
             sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             ctx = self._context(torch, dev, d)
+            t_ctx = time.perf_counter() - t0
             # the rank's rows with local column numbering
             g, st = dv["_assemble_call"][0], dv["_assemble_call"][1]
             s_indptr, _, s_data = dv["structural"]
@@ -153,12 +169,23 @@ class DistributedDGFEM:
             _lib.check(L.reyna_b200_csr_pattern_local(C.byref(g), C.byref(st), dg.polydegree, _ptr(indptr_local),
                                                       _ptr(indices_local), sp), "reyna_b200_csr_pattern_local")
             mg = C.c_void_p(None)
+            keep = []
             try:
                 if prec == "mg":
                     mo = _lib.RbMgOpts(nu=int(so.get("mg_nu", 3)), omega=float(so.get("mg_omega", 0.7)),
                                        alpha=float(so.get("mg_alpha", 1.8)))
+                    p0_indptr, p0_indices, p0_data = self._global_p0(torch, dev, dv)
+                    bounds32 = (C.c_int32 * (self.world + 1))(*[int(b) for b in self.bounds])
+                    keep += [p0_indptr, p0_indices, p0_data, bounds32]
+                    dd = _lib.RbMgDist(dist=ctx["handle"], rank=self.rank, world=self.world,
+                                       n_ghost_elem=fg.n_elem - fg.n_rows, n_global_elem=int(self.bounds[-1]),
+                                       bounds=C.cast(bounds32, C.c_void_p), p0_indptr=_ptr(p0_indptr),
+                                       p0_indices=_ptr(p0_indices), p0_data=_ptr(p0_data), p0_nnz=int(p0_data.numel()))
                     _lib.check(L.reyna_b200_mg_create(N, d, dg.polydegree, _ptr(indptr_local), _ptr(indices_local),
-                                                      _ptr(s_data), C.byref(mo), C.byref(mg), sp), "reyna_b200_mg_create")
+                                                      _ptr(s_data), C.byref(mo), C.byref(dd), C.byref(mg), sp),
+                               "reyna_b200_mg_create")
+                torch.cuda.synchronize()
+                t_setup = time.perf_counter() - t0
                 x = torch.zeros(N + n_ghost, dtype=torch.float64, device=dev)
                 ws_bytes = L.reyna_b200_solve_workspace(N, n_ghost, d)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -177,8 +204,45 @@ class DistributedDGFEM:
                                rel_residual=float(info.rel_residual), converged=bool(info.converged),
                                restarts=int(info.restarts), stagnated=bool(info.stagnated), world=self.world,
                                halo_exchanges=int(ex.value), allreduces=int(ar.value), n_ghost_elements=fg.n_elem - fg.n_rows,
-                               seconds=time.perf_counter() - t0)
+                               context_seconds=t_ctx, setup_seconds=t_setup, seconds=time.perf_counter() - t0)
         return sol
+
+    def _global_p0(self, torch, dev, dv):
+        """The GLOBAL piecewise-constant matrix A0 = (mode-(0,0) entry of every d x d block of B), replicated on every
+        rank: each rank extracts its rows (global element numbering) from its structural CSR and the rows are
+        all-gathered once per solve (8 B + 4 B per block: 0.1 GB at 1M elements)."""
+        import torch.distributed as dist
+        d = dv["d"]
+        s_indptr, s_indices, s_data = dv["structural"]          # global column numbering
+        N = dv["n"]
+        starts = s_indptr[0:N:d].to(torch.int64)                # first scalar row of every block row
+        nb = ((s_indptr[1:N + 1:d].to(torch.int64) - starts) // d)
+        rows = torch.repeat_interleave(torch.arange(nb.numel(), device=dev), nb)
+        first = torch.cumsum(nb, 0) - nb
+        pos = starts[rows] + (torch.arange(rows.numel(), device=dev) - first[rows]) * d
+        cols = (s_indices[pos] // d).to(torch.int32)
+        vals = s_data[pos].contiguous()
+        # all-gather (uneven): sizes first, then padded payloads
+        cnt = torch.tensor([cols.numel(), nb.numel()], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(cnts, cnt)
+        sizes = [int(c[0]) for c in cnts]
+        nrows = [int(c[1]) for c in cnts]
+        mx, mr = max(sizes), max(nrows)
+
+        def gather(t, n_each, width, dtype):
+            pad = torch.zeros(width, dtype=dtype, device=dev)
+            pad[:t.numel()] = t
+            outs = [torch.empty(width, dtype=dtype, device=dev) for _ in range(self.world)]
+            dist.all_gather(outs, pad)
+            return torch.cat([o[:n] for o, n in zip(outs, n_each)])
+
+        g_cols = gather(cols, sizes, mx, torch.int32)
+        g_vals = gather(vals, sizes, mx, torch.float64)
+        g_nb = gather(nb.to(torch.int32), nrows, mr, torch.int32)
+        g_indptr = torch.zeros(g_nb.numel() + 1, dtype=torch.int32, device=dev)
+        g_indptr[1:] = torch.cumsum(g_nb.to(torch.int64), 0).to(torch.int32)
+        return g_indptr, g_cols.contiguous(), g_vals.contiguous()
 
     def gather_solution(self) -> np.ndarray:
         """The global coefficient vector (element order of the unpartitioned geometry) on every rank."""

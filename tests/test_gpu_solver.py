@@ -38,7 +38,7 @@ def test_multigrid_operator_matches_scipy_restatement(rb, E, name, p):
     sp_ = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     mo = _lib.RbMgOpts(nu=3, omega=0.7, alpha=1.8)
     _lib.check(L.reyna_b200_mg_create(dv["n"], dv["d"], p, ip.data_ptr(), ix.data_ptr(), dat.data_ptr(), C.byref(mo),
-                                      C.byref(mg), sp_), "mg_create")
+                                      None, C.byref(mg), sp_), "mg_create")
     try:
         nl = C.c_int32(0)
         rows = (C.c_int32 * 16)()

@@ -208,7 +208,9 @@ int reyna_b200_mg_info(const rb_mg *mg, int32_t *n_levels, int32_t *level_rows /
 /* z = coarse-space correction of r (the multigrid part of the preconditioner alone; exposed for tests) */
 int reyna_b200_mg_apply(rb_mg *mg, const double *r, double *z, void *stream);
 
-size_t reyna_b200_solve_workspace(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d);
+/* nnz > 0 adds room for the block-column list that lets the SpMV of a block-structured matrix (blocked != 0) skip the
+ * per-entry column indices; with nnz == 0 the solver falls back to the generic CSR SpMV. */
+size_t reyna_b200_solve_workspace(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d, long long nnz);
 /* mg == NULL: block-Jacobi preconditioning only. */
 int reyna_b200_solve(int32_t n_rows_scalar, int32_t n_ghost_scalar, int32_t d, int blocked,
                      const int32_t *indptr, const int32_t *indices, const double *data,

@@ -142,7 +142,7 @@ def lib() -> C.CDLL:
     L.reyna_b200_compact_fill.restype = C.c_int
     L.reyna_b200_compact_fill.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp]
     L.reyna_b200_solve_workspace.restype = C.c_size_t
-    L.reyna_b200_solve_workspace.argtypes = [i32, i32, i32]
+    L.reyna_b200_solve_workspace.argtypes = [i32, i32, i32, C.c_longlong]
     L.reyna_b200_solve.restype = C.c_int
     L.reyna_b200_solve.argtypes = [i32, i32, i32, C.c_int, vp, vp, vp, vp, vp, C.POINTER(RbSolveOpts),
                                    C.POINTER(RbSolveInfo), vp, vp, vp, vp, vp, C.c_size_t, vp]

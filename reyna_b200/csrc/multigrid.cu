@@ -46,6 +46,7 @@ struct rb_mg {
     int has_p1 = 0;
     int32_t *p1_indptr = nullptr, *p1_indices = nullptr;
     double *p1_data = nullptr, *p1_minv = nullptr, *p1_r = nullptr, *p1_x = nullptr, *p1_t = nullptr;
+    int32_t* bcol = nullptr;       // block columns (element ids) of the fine / P1 block pattern
     double* p1_t0 = nullptr;       // distributed mode: this rank's P0 right-hand side before the all-gather
     int sel1[3] = {0, 1, 2};
     // P0 chain
@@ -288,12 +289,23 @@ __global__ void mg_prolong_add(int n, int agg, double alpha, const double* __res
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] += alpha * xc[i / agg];
 }
 
-// y = A^-1 x with the column-major inverse of mg_dense_inverse (one thread per row, coalesced over rows)
-__global__ void mg_dense_apply(int n, const double* __restrict__ invt, const double* __restrict__ x, double* __restrict__ y) {
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int k = 0; k < n; ++k) s = fma(invt[(size_t)k * n + r], x[k], s);
-        y[r] = s;
+// y = A^-1 x with the column-major inverse of mg_dense_inverse: a CTA of 256 threads = 8 k-slices x 32 rows, the partial
+// sums of the slices are combined in a fixed order through shared memory (n <= 256: a handful of CTAs, ~2 us)
+__global__ void __launch_bounds__(256) mg_dense_apply(int n, const double* __restrict__ invt, const double* __restrict__ x,
+                                                      double* __restrict__ y) {
+    __shared__ double s_part[8][33];
+    const int rl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int r = blockIdx.x * 32 + rl;
+    double s = 0.0;
+    if (r < n)
+        for (int k = sl; k < n; k += 8) s = fma(invt[(size_t)k * n + r], x[k], s);
+    s_part[sl][rl] = s;
+    __syncthreads();
+    if (sl == 0 && r < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += s_part[q][rl];
+        y[r] = t;
     }
 }
 
@@ -327,6 +339,31 @@ __global__ void __launch_bounds__(kMgThreads) mg_residual(int n, int ncols, cons
     }
 }
 
+// t = b - A x for the 3 x 3-block P1 matrix without reading its column indices (block columns shared with the fine level)
+template <int G>
+__global__ void __launch_bounds__(kMgThreads) mg_residual_blocked3(int n, int ncols, const int32_t* __restrict__ indptr,
+                                                                   const int32_t* __restrict__ bcol,
+                                                                   const double* __restrict__ data, const double* __restrict__ b,
+                                                                   const double* __restrict__ x, double* __restrict__ t) {
+    const int lane = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += stride) {
+        const int e = (int)(i / 3);
+        const int lo = indptr[i], len = indptr[i + 1] - lo;
+        const int32_t* bc = bcol + indptr[e * 3] / 9;
+        const double* dr = data + lo;
+        double s = 0.0;
+        for (int k = lane; k < len; k += G) {
+            const int sb = k / 3, c = bc[sb] * 3 + (k - sb * 3);
+            if (c < ncols) s = fma(dr[k], x[c], s);
+        }
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) s += __shfl_xor_sync(gm, s, o, G);
+        if (lane == 0) t[i] = b[i] - s;
+    }
+}
+
 // coarse[e*dc + jc] = fine[e*d + sel[jc]]
 __global__ void mg_select(int n_elem, int d, int dc, int s0, int s1, int s2, const double* __restrict__ fine,
                           double* __restrict__ coarse) {
@@ -347,6 +384,8 @@ __global__ void mg_pad_add(int n_elem, int d, int dc, int s0, int s1, int s2, co
     }
 }
 
+int launch_block_columns(int n_block_rows, int d, const int32_t* indptr, const int32_t* indices, int32_t* bcol,
+                         cudaStream_t st);   // solver.cu
 void block_jacobi_setup_launch(int n_blocks, int d, const int32_t* indptr, const int32_t* indices, const double* data,
                                double* minv, int* singular, cudaStream_t st);   // solver.cu
 
@@ -356,7 +395,7 @@ static inline int mg_grid(int64_t n) { return grid_for(n, kMgThreads, kNumSMs * 
 static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     MgLevel& L = mg->lev[k];
     if (k == mg->nlev - 1) {
-        mg_dense_apply<<<grid_for(L.n, 128, kNumSMs), 128, 0, st>>>(L.n, mg->dense_inv, L.b, L.x);
+        mg_dense_apply<<<(L.n + 31) / 32, 256, 0, st>>>(L.n, mg->dense_inv, L.b, L.x);
         RB_LAUNCH_CHECK("mg_dense_apply");
         return 0;
     }
@@ -416,8 +455,8 @@ int mg_apply_add(rb_mg* mg, const double* r, double* z, cudaStream_t st) {
         mg_block_apply<false><<<g1, kMgThreads, 0, st>>>(n1, 3, mg->p1_minv, mg->p1_r, mg->p1_x);          // pre-smoothing
         RB_LAUNCH_CHECK("mg p1 pre");
         if (dist && (rc = dist_halo_d(mg->dist, mg->p1_x, 3, st))) return rc;
-        mg_residual<8><<<mg_grid((int64_t)n1 * 8), kMgThreads, 0, st>>>(n1, nc1, mg->p1_indptr, mg->p1_indices, mg->p1_data,
-                                                                       mg->p1_r, mg->p1_x, mg->p1_t);
+        mg_residual_blocked3<8><<<mg_grid((int64_t)n1 * 8), kMgThreads, 0, st>>>(n1, nc1, mg->p1_indptr, mg->bcol, mg->p1_data,
+                                                                                mg->p1_r, mg->p1_x, mg->p1_t);
         mg_select<<<mg_grid(E), kMgThreads, 0, st>>>(E, 3, 1, 0, 0, 0, mg->p1_t, b0_local);
         RB_LAUNCH_CHECK("mg p1 down");
     } else {
@@ -434,8 +473,8 @@ int mg_apply_add(rb_mg* mg, const double* r, double* z, cudaStream_t st) {
         mg_pad_add<<<mg_grid(E), kMgThreads, 0, st>>>(E, 3, 1, 0, 0, 0, x0_local, mg->p1_x);
         RB_LAUNCH_CHECK("mg_pad_add");
         if (dist && (rc = dist_halo_d(mg->dist, mg->p1_x, 3, st))) return rc;
-        mg_residual<8><<<mg_grid((int64_t)n1 * 8), kMgThreads, 0, st>>>(n1, nc1, mg->p1_indptr, mg->p1_indices, mg->p1_data,
-                                                                       mg->p1_r, mg->p1_x, mg->p1_t);
+        mg_residual_blocked3<8><<<mg_grid((int64_t)n1 * 8), kMgThreads, 0, st>>>(n1, nc1, mg->p1_indptr, mg->bcol, mg->p1_data,
+                                                                                mg->p1_r, mg->p1_x, mg->p1_t);
         mg_block_apply<true><<<g1, kMgThreads, 0, st>>>(n1, 3, mg->p1_minv, mg->p1_t, mg->p1_x);           // post-smoothing
         mg_pad_add<<<g1, kMgThreads, 0, st>>>(E, d, 3, s0, s1, s2, mg->p1_x, z);
         RB_LAUNCH_CHECK("mg p1 up");
@@ -520,6 +559,8 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
         if ((rc = dev_alloc(mg, (void**)&mg->p1_t, sizeof(double) * (size_t)n1))) return fail(rc);
         mg_extract_modes<<<mg_grid(n1), kMgThreads, 0, st>>>(E, d, 3, mg->sel1[0], mg->sel1[1], mg->sel1[2], indptr, indices,
                                                             data, mg->p1_indptr, mg->p1_indices, mg->p1_data);
+        if ((rc = dev_alloc(mg, (void**)&mg->bcol, sizeof(int32_t) * (size_t)(nblocks + 1)))) return fail(rc);
+        if ((rc = launch_block_columns(E, d, indptr, indices, mg->bcol, st))) return fail(rc);
         int* sing = nullptr;
         if ((rc = dev_alloc(mg, (void**)&sing, sizeof(int)))) return fail(rc);
         cudaMemsetAsync(sing, 0, sizeof(int), st);

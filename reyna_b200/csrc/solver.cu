@@ -54,6 +54,65 @@ static int launch_spmv(int n, int64_t nnz_hint, const int32_t* indptr, const int
     return 0;
 }
 
+// Block-structured variant: the matrix of reyna_b200_csr_pattern stores, per block row, nb blocks of D x D entries with D
+// consecutive columns each, so the column of entry k of a scalar row is bcol[first_block + k / D] * D + k % D -- the
+// 4-byte column index per entry (a third of the SpMV traffic) is replaced by one int per D*D entries.
+__global__ void block_columns_kernel(int n_blocks_rows, int d, const int32_t* __restrict__ indptr,
+                                     const int32_t* __restrict__ indices, int32_t* __restrict__ bcol) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_blocks_rows; e += gridDim.x * blockDim.x) {
+        const int f0 = indptr[e * d];
+        const int nb = (indptr[e * d + 1] - f0) / d;
+        const int b0 = f0 / (d * d);
+        for (int s = 0; s < nb; ++s) bcol[b0 + s] = indices[f0 + s * d] / d;
+    }
+}
+
+template <int G, int D>
+__global__ void __launch_bounds__(256) spmv_blocked_kernel(int n, const int32_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ bcol,
+                                                           const double* __restrict__ data, const double* __restrict__ x,
+                                                           double* __restrict__ y) {
+    const int lane = threadIdx.x % G;
+    const int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    for (int64_t r = row0; r < n; r += stride) {
+        const int e = (int)(r / D);
+        const int lo = indptr[r], len = indptr[r + 1] - lo;
+        const int32_t* bc = bcol + indptr[e * D] / (D * D);
+        const double* dr = data + lo;
+        double s = 0.0;
+        for (int k = lane; k < len; k += G) {
+            const int sb = k / D, i = k - sb * D;
+            s = fma(dr[k], x[bc[sb] * D + i], s);
+        }
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) s += __shfl_xor_sync(gmask, s, o, G);
+        if (lane == 0) y[r] = s;
+    }
+}
+
+int launch_block_columns(int n_block_rows, int d, const int32_t* indptr, const int32_t* indices, int32_t* bcol,
+                         cudaStream_t st) {
+    block_columns_kernel<<<grid_for(n_block_rows, 256, kNumSMs * 8), 256, 0, st>>>(n_block_rows, d, indptr, indices, bcol);
+    RB_LAUNCH_CHECK("block_columns_kernel");
+    return 0;
+}
+
+static int launch_spmv_blocked(int n, int d, const int32_t* indptr, const int32_t* bcol, const double* data,
+                               const double* x, double* y, cudaStream_t st) {
+    const int blocks_cap = kNumSMs * 16;
+    const int g = grid_for((int64_t)n * 8, 256, blocks_cap);
+    switch (d) {
+        case 3: spmv_blocked_kernel<8, 3><<<g, 256, 0, st>>>(n, indptr, bcol, data, x, y); break;
+        case 6: spmv_blocked_kernel<8, 6><<<g, 256, 0, st>>>(n, indptr, bcol, data, x, y); break;
+        case 10: spmv_blocked_kernel<16, 10><<<grid_for((int64_t)n * 16, 256, blocks_cap), 256, 0, st>>>(n, indptr, bcol, data, x, y); break;
+        default: return -1;
+    }
+    RB_LAUNCH_CHECK("spmv_blocked_kernel");
+    return 0;
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // block-Jacobi
 // ----------------------------------------------------------------------------------------------------------------
@@ -318,18 +377,56 @@ struct Solver {
         return 0;
     }
     rb_mg* mg = nullptr;
-    // z = M^-1 v: block Jacobi, plus the multigrid coarse-space correction when a hierarchy is attached
-    int precond(const double* v, double* z) {
+    const int32_t* bcol = nullptr;     // block columns of the structural pattern (blocked SpMV), or null
+    bool use_graphs = false;           // single-GPU: the (long, launch-bound) multigrid application is replayed as a CUDA graph
+    struct PrecGraph { const double* v; double* z; cudaGraphExec_t exec; };
+    PrecGraph graphs[4];
+    int n_graphs = 0;
+
+    int precond_launch(const double* v, double* z) {
         k_precond<<<nb, kVecThreads, 0, st>>>(n, d, minv, v, z);
         RB_LAUNCH_CHECK("k_precond");
         if (mg) return mg_apply_add(mg, v, z, st);
         return 0;
+    }
+    // z = M^-1 v: block Jacobi, plus the multigrid coarse-space correction when a hierarchy is attached
+    int precond(const double* v, double* z) {
+        if (!use_graphs || !mg) return precond_launch(v, z);
+        for (int i = 0; i < n_graphs; ++i)
+            if (graphs[i].v == v && graphs[i].z == z) {
+                RB_CUDA(cudaGraphLaunch(graphs[i].exec, st));
+                count_launch();
+                return 0;
+            }
+        if (n_graphs == 4) return precond_launch(v, z);
+        cudaGraph_t graph = nullptr;
+        RB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = precond_launch(v, z);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc || ce != cudaSuccess || !graph) {          // capture unavailable: fall back to plain launches
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            use_graphs = false;
+            return precond_launch(v, z);
+        }
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { cudaGetLastError(); use_graphs = false; return precond_launch(v, z); }
+        graphs[n_graphs++] = PrecGraph{v, z, exec};
+        RB_CUDA(cudaGraphLaunch(exec, st));
+        return 0;
+    }
+    void destroy_graphs() {
+        for (int i = 0; i < n_graphs; ++i) cudaGraphExecDestroy(graphs[i].exec);
+        n_graphs = 0;
     }
     int spmv(double* xin, double* yout) {
         if (halo) {
             int rc = halo(user, xin, (void*)st);
             if (rc) { set_error("halo callback failed (%d)", rc); return rc; }
         }
+        if (bcol && launch_spmv_blocked(n, d, indptr, bcol, data, xin, yout, st) == 0) return 0;
         return launch_spmv(n, nnz, indptr, indices, data, xin, yout, st);
     }
 };
@@ -340,7 +437,8 @@ using namespace rb;
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-extern "C" size_t reyna_b200_solve_workspace(int32_t n, int32_t n_ghost, int32_t d) {
+extern "C" size_t reyna_b200_solve_workspace(int32_t n, int32_t n_ghost, int32_t d, long long nnz) {
+    // nnz > 0: room for the block-column list of the blocked SpMV (one int per d*d entries)
     const size_t full = align256(sizeof(double) * ((size_t)n + n_ghost));
     const size_t own = align256(sizeof(double) * (size_t)n);
     size_t b = 0;
@@ -350,6 +448,7 @@ extern "C" size_t reyna_b200_solve_workspace(int32_t n, int32_t n_ghost, int32_t
     b += align256(sizeof(double) * 3 * kMaxPartials);
     b += align256(sizeof(double) * 16) * 2;          // red, S
     b += 256;                                        // singular flag
+    b += align256(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz / ((long long)d * d) + 1 : 1));   // block columns
     return b;
 }
 
@@ -365,11 +464,11 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
                                 const rb_solve_opts* opts, rb_solve_info* info, rb_halo_fn halo,
                                 rb_allreduce_fn allreduce, void* user, rb_mg* mg, void* workspace,
                                 size_t workspace_bytes, void* stream) {
-    (void)blocked;
+    int rc0 = 0;
     RB_REQUIRE(indptr && indices && data && rhs && x && opts && info && workspace, RB_E_ARG,
                "reyna_b200_solve: null argument");
     RB_REQUIRE(d >= 1 && d <= kMaxD && n % d == 0, RB_E_ARG, "reyna_b200_solve: bad block size");
-    RB_REQUIRE(workspace_bytes >= reyna_b200_solve_workspace(n, n_ghost, d), RB_E_WORKSPACE,
+    RB_REQUIRE(workspace_bytes >= reyna_b200_solve_workspace(n, n_ghost, d, 0), RB_E_WORKSPACE,
                "reyna_b200_solve: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     info->iterations = 0;
@@ -399,6 +498,7 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     s.red = (double*)take(align256(sizeof(double) * 16));
     s.S = (double*)take(align256(sizeof(double) * 16));
     s.singular = (int*)take(256);
+    int32_t* bcol_buf = (int32_t*)take(align256(sizeof(int32_t) * (size_t)(s.nnz / ((int64_t)d * d) + 1)));
     s.nb = grid_for(n, kVecThreads, kMaxPartials);
     const int nb = s.nb;
     RB_CUDA(cudaMemsetAsync(s.singular, 0, sizeof(int), st));
@@ -406,6 +506,12 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     RB_CUDA(cudaMemsetAsync(s.v, 0, own, st));
 
     block_jacobi_setup_launch(n / d, d, indptr, indices, data, s.minv, s.singular, st);
+    if (blocked && (d == 3 || d == 6 || d == 10) &&
+        workspace_bytes >= reyna_b200_solve_workspace(n, n_ghost, d, s.nnz)) {
+        if ((rc0 = launch_block_columns(n / d, d, indptr, indices, bcol_buf, st))) return rc0;
+        s.bcol = bcol_buf;
+    }
+    s.use_graphs = (halo == nullptr);
     RB_LAUNCH_CHECK("block_jacobi_setup");
 
     int rc;
@@ -528,6 +634,7 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     int sing = 0;
     RB_CUDA(cudaMemcpyAsync(&sing, s.singular, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
+    s.destroy_graphs();
     info->iterations = it;
     info->rel_residual = sqrt(rr / (bb > 0.0 ? bb : 1.0));
     info->converged = done ? 1 : 0;

@@ -446,7 +446,7 @@ class DGFEM:
                     mg_levels = [int(rows[i]) for i in range(nl.value)]
                 setup_s = time.perf_counter() - t0
                 x = torch.zeros(N, dtype=torch.float64, device=dev)
-                ws_bytes = L.reyna_b200_solve_workspace(N, 0, d)
+                ws_bytes = L.reyna_b200_solve_workspace(N, 0, d, int(s_data.numel()))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 _lib.check(L.reyna_b200_solve(N, 0, d, 1, _ptr(s_indptr), _ptr(s_indices), _ptr(s_data), _ptr(dv['load']),
                                               _ptr(x), C.byref(opts), C.byref(info), None, None, None, mg, _ptr(ws),

@@ -187,7 +187,7 @@ class DistributedDGFEM:
                 torch.cuda.synchronize()
                 t_setup = time.perf_counter() - t0
                 x = torch.zeros(N + n_ghost, dtype=torch.float64, device=dev)
-                ws_bytes = L.reyna_b200_solve_workspace(N, n_ghost, d)
+                ws_bytes = L.reyna_b200_solve_workspace(N, n_ghost, d, int(s_data.numel()))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 halo = C.cast(L.reyna_b200_nccl_halo, C.c_void_p)
                 allr = C.cast(L.reyna_b200_nccl_allreduce, C.c_void_p)

@@ -400,7 +400,11 @@ struct Solver {
             }
         if (n_graphs == 4) return precond_launch(v, z);
         cudaGraph_t graph = nullptr;
-        RB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();                            // e.g. the legacy default stream cannot be captured
+            use_graphs = false;
+            return precond_launch(v, z);
+        }
         int rc = precond_launch(v, z);
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc || ce != cudaSuccess || !graph) {          // capture unavailable: fall back to plain launches

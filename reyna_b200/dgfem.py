@@ -433,7 +433,12 @@ class DGFEM:
         mg = C.c_void_p(None)
         mg_levels = None
         with torch.cuda.device(dev):
-            sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            # a side stream: the library replays the multigrid application as a CUDA graph, which the legacy default
+            # stream cannot capture
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            torch.cuda.set_stream(side)
+            sp = C.c_void_p(side.cuda_stream)
             try:
                 if prec == 'mg':
                     mo = _lib.RbMgOpts(nu=int(so.get('mg_nu', 3)), omega=float(so.get('mg_omega', 0.7)),
@@ -451,8 +456,10 @@ class DGFEM:
                 _lib.check(L.reyna_b200_solve(N, 0, d, 1, _ptr(s_indptr), _ptr(s_indices), _ptr(s_data), _ptr(dv['load']),
                                               _ptr(x), C.byref(opts), C.byref(info), None, None, None, mg, _ptr(ws),
                                               ws_bytes, sp), 'reyna_b200_solve')
+                side.synchronize()
                 sol = x.cpu().numpy()
             finally:
+                torch.cuda.set_stream(torch.cuda.default_stream(dev))
                 if mg.value:
                     L.reyna_b200_mg_destroy(mg)
         self.solve_info = dict(method=method, iterations=int(info.iterations), rel_residual=float(info.rel_residual),

@@ -260,6 +260,12 @@ size_t reyna_b200_errors_workspace(void);
 int reyna_b200_errors(const rb_geom *g, const rb_quad *q, const rb_err_samples *s, double sigma_D,
                       const double *solution, double *out3, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Point evaluation of the DG solution (replaces tools.evaluate, reyna/DGFEM/two_dimensional/tools.py:117-153), batched:
+ * out[i] = u_h(xy[i]) on element elem[i] (the points must lie in / on their elements, as upstream requires).
+ * bbox [n_elem][4], xy [n_points][2], elem [n_points], solution [n_elem*d], out [n_points]: device pointers. */
+int reyna_b200_evaluate(int p, int32_t n_points, const double *bbox, const double *xy, const int32_t *elem,
+                        const double *solution, double *out, void *stream);
+
 /* FP64 FMA micro-benchmark used as the compute roofline denominator: runs `iters` dependent-chain FMAs on every
  * lane of a full grid and returns the flop count through *flops (host). */
 int reyna_b200_fma_probe(int iters, double *scratch_dev, double *flops, void *stream);

@@ -27,7 +27,7 @@ namespace rb {
 namespace elem {
 
 constexpr int kWarp = 32;          // elements per CTA: every warp is its own CTA, so a finished warp frees its slot at once
-constexpr int kSortChunk = 512;    // elements sorted together by number of faces (lane balance vs locality)
+constexpr int kSortChunk = 128;    // elements sorted together by number of faces (lane balance vs locality)
 
 template <int P, int RS>
 struct Dims {

@@ -219,6 +219,26 @@ __global__ void __launch_bounds__(32) err_final_kernel(const double* __restrict_
     }
 }
 
+// ---- point evaluation of the DG solution (replaces tools.evaluate, reyna/DGFEM/two_dimensional/tools.py:117-153) ------
+// out[i] = sum_k u[elem[i]*d + k] phi_k^{elem[i]}(x_i); bbox-scaled tensor-Legendre basis exactly as in the assembly
+template <int P>
+__global__ void __launch_bounds__(256) eval_points_kernel(int n_points, const double* __restrict__ bbox,
+                                                          const double* __restrict__ xy, const int32_t* __restrict__ elem,
+                                                          const double* __restrict__ u, LegConst lc, double* __restrict__ out) {
+    constexpr int D = BasisDim<P>::D;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += gridDim.x * blockDim.x) {
+        const int e = elem[i];
+        const ElemBox bx = make_box(bbox, e);
+        const double2 pt = reinterpret_cast<const double2*>(xy)[i];
+        double phi[D], gx[D], gy[D];
+        eval_basis<P, false>(pt.x, pt.y, bx, lc, phi, gx, gy);
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fma(phi[k], u[(size_t)e * D + k], s);
+        out[i] = s;
+    }
+}
+
 template <int P>
 static int launch_errors(const ErrArgs& A, bool diff, cudaStream_t st) {
     if (A.g.n_tri > 0) {
@@ -278,5 +298,22 @@ extern "C" int reyna_b200_errors(const rb_geom* g, const rb_quad* q, const rb_er
     if (rc) return rc;
     err_final_kernel<<<1, 32, 0, st>>>(A.partial, out3);
     RB_LAUNCH_CHECK("err_final_kernel");
+    return 0;
+}
+
+extern "C" int reyna_b200_evaluate(int p, int32_t n_points, const double* bbox, const double* xy, const int32_t* elem,
+                                   const double* solution, double* out, void* stream) {
+    RB_REQUIRE(bbox && xy && elem && solution && out, RB_E_ARG, "reyna_b200_evaluate: null argument");
+    RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_evaluate: polynomial degree must be 1..3");
+    if (n_points <= 0) return 0;
+    const LegConst lc = make_leg_const();
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = grid_for(n_points, 256, kNumSMs * 8);
+    switch (p) {
+        case 1: eval_points_kernel<1><<<blocks, 256, 0, st>>>(n_points, bbox, xy, elem, solution, lc, out); break;
+        case 2: eval_points_kernel<2><<<blocks, 256, 0, st>>>(n_points, bbox, xy, elem, solution, lc, out); break;
+        default: eval_points_kernel<3><<<blocks, 256, 0, st>>>(n_points, bbox, xy, elem, solution, lc, out); break;
+    }
+    RB_LAUNCH_CHECK("eval_points_kernel");
     return 0;
 }

@@ -275,8 +275,8 @@ constexpr int kMaxNb = 64;   // neighbours per element held in shared memory (po
 
 // one warp per block row: every scalar row (e,j) of the block row has the same column list, so it is built once in
 // shared memory and streamed d times to the contiguous index range of the block row
-template <bool LOCAL>
-__global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows, int d, const int32_t* __restrict__ ielem,
+template <bool LOCAL, int D>
+__global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows, int d_runtime, const int32_t* __restrict__ ielem,
                                                                      const int32_t* __restrict__ adj_nb,
                                                                      const int32_t* __restrict__ gid,
                                                                      const int32_t* __restrict__ adj_off,
@@ -285,8 +285,10 @@ __global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows,
                                                                      int32_t* __restrict__ indptr,
                                                                      int32_t* __restrict__ indices) {
     __shared__ int s_nb[kPatWarps][kMaxNb + 1];
+    constexpr int d = D;               // compile-time: the index arithmetic below divides by it
+    (void)d_runtime;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int dd = d * d;
+    constexpr int dd = d * d;
     for (int e = blockIdx.x * kPatWarps + w; e < n_rows; e += gridDim.x * kPatWarps) {
         const int lo = adj_off[e], hi = adj_off[e + 1];
         const int g0 = grp_off[e];
@@ -324,12 +326,28 @@ __global__ void __launch_bounds__(kPatWarps * 32) csr_pattern_kernel(int n_rows,
         const int rowlen = nb * d;
         if (lane < d) indptr[(int64_t)e * d + lane] = (int32_t)(base + (int64_t)lane * rowlen);
         const int total = d * rowlen;
-        int r = lane % rowlen;              // position inside the row template
-        for (int k = lane; k < total; k += 32) {
-            const int slot = r / d;
-            indices[base + k] = s_nb[w][slot] * d + (r - slot * d);
-            r += 32;
-            while (r >= rowlen) r -= rowlen;
+        if ((dd & 3) == 0) {
+            // 16-byte stores: the block row starts at a multiple of d*d ints (d*d % 4 == 0) and holds a multiple of 4 ints
+            int4* out4 = reinterpret_cast<int4*>(indices + base);
+            for (int k4 = lane; k4 < (total >> 2); k4 += 32) {
+                int r = (k4 << 2) % rowlen;          // position inside the row template
+                int v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int slot = r / d;
+                    v[j] = s_nb[w][slot] * d + (r - slot * d);
+                    if (++r == rowlen) r = 0;
+                }
+                out4[k4] = make_int4(v[0], v[1], v[2], v[3]);
+            }
+        } else {
+            int r = lane % rowlen;
+            for (int k = lane; k < total; k += 32) {
+                const int slot = r / d;
+                indices[base + k] = s_nb[w][slot] * d + (r - slot * d);
+                r += 32;
+                while (r >= rowlen) r -= rowlen;
+            }
         }
         __syncwarp();
     }
@@ -380,17 +398,29 @@ __global__ void compact_fill_kernel(int n, const int32_t* __restrict__ indptr, c
 
 }  // namespace rb
 
+template <bool LOCAL>
+static int launch_pattern(const rb_geom* g, const rb_structure* s, int p, int d, int blocks, int32_t* indptr, int32_t* indices,
+                          cudaStream_t st) {
+#define RB_PATTERN(DD)                                                                                                   \
+    rb::csr_pattern_kernel<LOCAL, DD><<<blocks, rb::kPatWarps * 32, 0, st>>>(g->n_rows, d, g->ielem, s->adj_nb, g->elem_gid, \
+                                                                             s->adj_off, s->adj_item, s->grp_off, indptr, indices)
+    switch (p) {
+        case 1: RB_PATTERN(3); break;
+        case 2: RB_PATTERN(6); break;
+        default: RB_PATTERN(10); break;
+    }
+#undef RB_PATTERN
+    RB_LAUNCH_CHECK("csr_pattern_kernel");
+    return 0;
+}
+
 extern "C" int reyna_b200_csr_pattern(const rb_geom* g, const rb_structure* s, int p, int32_t* indptr,
                                       int32_t* indices, void* stream) {
     RB_REQUIRE(g && s && indptr && indices, RB_E_ARG, "reyna_b200_csr_pattern: null argument");
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_csr_pattern: polynomial degree must be 1..3");
     const int d = (p + 1) * (p + 2) / 2;
     const int blocks = grid_for(g->n_rows, kPatWarps, kNumSMs * 8);
-    csr_pattern_kernel<false><<<blocks, kPatWarps * 32, 0, (cudaStream_t)stream>>>(g->n_rows, d, g->ielem, s->adj_nb, g->elem_gid,
-                                                                                     s->adj_off, s->adj_item, s->grp_off, indptr,
-                                                                                     indices);
-    RB_LAUNCH_CHECK("csr_pattern_kernel");
-    return 0;
+    return launch_pattern<false>(g, s, p, d, blocks, indptr, indices, (cudaStream_t)stream);
 }
 
 extern "C" int reyna_b200_csr_pattern_local(const rb_geom* g, const rb_structure* s, int p, int32_t* indptr,
@@ -399,11 +429,7 @@ extern "C" int reyna_b200_csr_pattern_local(const rb_geom* g, const rb_structure
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_csr_pattern_local: polynomial degree must be 1..3");
     const int d = (p + 1) * (p + 2) / 2;
     const int blocks = grid_for(g->n_rows, kPatWarps, kNumSMs * 8);
-    csr_pattern_kernel<true><<<blocks, kPatWarps * 32, 0, (cudaStream_t)stream>>>(g->n_rows, d, g->ielem, s->adj_nb, g->elem_gid,
-                                                                                    s->adj_off, s->adj_item, s->grp_off, indptr,
-                                                                                    indices);
-    RB_LAUNCH_CHECK("csr_pattern_kernel<local>");
-    return 0;
+    return launch_pattern<true>(g, s, p, d, blocks, indptr, indices, (cudaStream_t)stream);
 }
 
 extern "C" size_t reyna_b200_compact_workspace(int32_t n_scalar_rows) {

@@ -482,6 +482,15 @@ class DGFEM:
         from .errors import dg_errors
         return dg_errors(self, exact_solution, grad_exact_solution, div_advection)
 
+    def evaluate(self, points: np.ndarray, elements: np.ndarray) -> np.ndarray:
+        """u_h at ``points[i]`` (which must lie in element ``elements[i]``), batched on the device -- the many-element form
+        of tools.evaluate (tools.py:117-153)."""
+        if self.solution is None:
+            raise ValueError('Need to run the .dgfem() method to generate a solution before evaluating it.')
+        from .tools import evaluate_batch
+        return evaluate_batch(points, elements, self.solution, self.geometry.elem_bounding_boxes, self.polydegree,
+                              device=self.device)
+
     def plot_DG(self):
         if self.solution is None:
             raise ValueError("Need to provide a solution using either the method '.dgfem' or an external function.")

@@ -283,3 +283,27 @@ def test_partitioned_assembly_equals_global_rows(rb, world, name, p):
     assert np.array_equal(B.indptr, ref.B.indptr) and np.array_equal(B.indices, ref.B.indices)
     assert np.array_equal(B.data, ref.B.data)
     assert np.array_equal(np.concatenate(loads), np.asarray(ref.L.todense()).reshape(-1))
+
+
+def test_evaluate_matches_oracle_basis(rb):
+    """tools.evaluate (tools.py:117-153): element-wise signature and the batched form, against the oracle's basis."""
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(300, seed=12), subtriangulation="fan")
+    for p in (1, 2, 3):
+        dg = _run(rb, geo, "adr", p)
+        orders = dg_oracle.basis_orders(p)
+        d = orders.shape[0]
+        rng = np.random.default_rng(p)
+        el = rng.integers(0, geo.n_elements, 500)
+        bb = np.asarray(geo.elem_bounding_boxes)[el]
+        # points inside the bounding boxes of their elements (the basis is defined there)
+        pts = np.column_stack((bb[:, 0] + rng.random(500) * (bb[:, 1] - bb[:, 0]), bb[:, 2] + rng.random(500) * (bb[:, 3] - bb[:, 2])))
+        phi, _ = dg_oracle.basis_and_grad(pts, bb, orders, need_grad=False)
+        want = np.einsum("kn,nk->n", phi, dg.solution.reshape(-1, d)[el])
+        got = dg.evaluate(pts, el)
+        assert util.rel_inf(got, want) <= 1e-13
+        e0 = int(el[0])
+        mask = el == e0
+        one = rb.evaluate(pts[mask], dg.solution[e0 * d:(e0 + 1) * d], np.asarray(geo.elem_bounding_boxes)[e0], orders=orders)
+        assert util.rel_inf(one, want[mask]) <= 1e-13
+        assert np.allclose(rb.evaluate(pts[mask], dg.solution[e0 * d:(e0 + 1) * d], np.asarray(geo.elem_bounding_boxes)[e0]), one)

@@ -307,3 +307,28 @@ def test_evaluate_matches_oracle_basis(rb):
         one = rb.evaluate(pts[mask], dg.solution[e0 * d:(e0 + 1) * d], np.asarray(geo.elem_bounding_boxes)[e0], orders=orders)
         assert util.rel_inf(one, want[mask]) <= 1e-13
         assert np.allclose(rb.evaluate(pts[mask], dg.solution[e0 * d:(e0 + 1) * d], np.asarray(geo.elem_bounding_boxes)[e0]), one)
+
+
+def _kinked_mesh(rb):
+    """2 x 2 polygons whose common borders are POLYLINES (two collinear-free edges each): neighbouring elements share two
+    interior faces, so the (element, face) adjacency contains repeated neighbours that must merge into one CSR block."""
+    v = np.array([[0.0, 0.0], [0.5, 0.0], [1.0, 0.0], [0.0, 0.5], [0.45, 0.25], [0.55, 0.75], [1.0, 0.5], [0.0, 1.0],
+                  [0.5, 1.0], [1.0, 1.0], [0.5, 0.5], [0.25, 0.55], [0.75, 0.45]])
+    regions = [np.array([0, 1, 4, 10, 11, 3]), np.array([1, 2, 6, 12, 10, 4]), np.array([3, 11, 10, 5, 8, 7]),
+               np.array([10, 12, 6, 9, 8, 5])]
+    pts = np.array([[0.22, 0.25], [0.78, 0.22], [0.22, 0.78], [0.78, 0.75]])
+    return rb.PolyMesh(v, regions, pts, None)
+
+
+@pytest.mark.parametrize("name,p", [("variable", 1), ("variable", 2), ("variable_hyperbolic", 2), ("adr", 3)])
+def test_repeated_neighbours_merge_into_one_block(rb, name, p):
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(_kinked_mesh(rb))
+    assert geo.interior_edges.shape[0] == 8                  # every pair of neighbours shares two faces
+    dg = _run(rb, geo, name, p)
+    assert dg._dev["structure"]["n_dup_items"] > 0
+    B, L, info = dg_oracle.assemble(geo, p, **PROBLEMS[name]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
+    assert util.rel_l2(dg.solution, dg_oracle.solve(B, L)) <= util.TOL_SOLUTION

@@ -74,6 +74,7 @@ class DGFEM:
         self.device = None         # torch device; default: current CUDA device
         self.keep_device_inputs = False   # bench.py: keep the uploaded samples for kernel-only timing
         self._inputs = None
+        self._side_streams = {}
         self._pinned = {}          # cached pinned staging buffers (host side of the coefficient upload)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -306,6 +307,7 @@ class DGFEM:
             flags, bnd_elem, bnd_off, bnd_face = self._boundary_lists(fg)
             bd = {k: torch.from_numpy(v).to(dev) for k, v in
                   dict(flags=flags, bnd_elem=bnd_elem, bnd_off=bnd_off, bnd_face=bnd_face).items()}
+            bd['has_spill'] = bool((flags & 4).any())
             tm['h2d_bytes'] = int(nbytes)
             tm['coefficient_eval_upload_s'] = time.perf_counter() - t1
 
@@ -354,8 +356,17 @@ class DGFEM:
         data = torch.empty(nnz, **f64)
         load = torch.empty(N, **f64)
         zero_count = torch.zeros(1, dtype=torch.int64, device=dev)
-        _lib.check(L.reyna_b200_csr_pattern(C.byref(g), C.byref(st), p, _ptr(indptr), _ptr(indices), sp),
-                   'reyna_b200_csr_pattern')
+        # the index arrays only depend on the structure: they are written on a side stream while the (occupancy-limited,
+        # 8 warps per SM) assembly kernel runs, and joined before the step ends
+        main_stream = torch.cuda.current_stream()
+        side = self._side_streams.get(str(dev))
+        if side is None:
+            side = self._side_streams[str(dev)] = torch.cuda.Stream(device=dev)
+        side.wait_stream(main_stream)
+        _lib.check(L.reyna_b200_csr_pattern(C.byref(g), C.byref(st), p, _ptr(indptr), _ptr(indices),
+                                            C.c_void_p(side.cuda_stream)), 'reyna_b200_csr_pattern')
+        indptr.record_stream(side)
+        indices.record_stream(side)
         aws_bytes = L.reyna_b200_assemble_workspace(E, fg.n_iface)
         aws = torch.empty(aws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(L.reyna_b200_assemble(C.byref(g), C.byref(st), C.byref(co), C.byref(q), float(self.sigma_D),
@@ -368,12 +379,13 @@ class DGFEM:
                                              n_bnd, _ptr(bd['bnd_elem']), _ptr(bd['bnd_off']), _ptr(bd['bnd_face']),
                                              _ptr(bd['flags']), _ptr(data), _ptr(load), _ptr(spill),
                                              _ptr(zero_count), sp), 'reyna_b200_boundary')
-        if bool((bd['flags'] & 4).any()):
+        if bd.get('has_spill', False):
             if getattr(fg, 'elem_gid', None) is not None:
                 raise _lib.ReynaB200Error('partitioned assembly does not mirror the reference index quirk of main.py:397-400 '
                                           '(boundary edges that are only partly elliptic)')
             data[0] -= spill.sum()          # the reference's B[0,0] quirk (main.py:397-400)
             zero_count += (data[0] == 0).to(torch.int64)
+        main_stream.wait_stream(side)
         blocked = True
         structural_data = data
         structural = (indptr, indices, data)        # the solver (and its multigrid hierarchy) works on the block pattern

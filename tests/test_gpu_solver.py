@@ -98,3 +98,24 @@ def test_block_jacobi_still_available(rb):
     dg.solver_options.update(preconditioner="mg")
     dg.dgfem(solve=True)
     assert dg.solve_info["iterations"] < bj_its
+
+
+def test_solution_matches_spsolve_at_config3a(rb):
+    """BASELINE config 3a (65 536 elements, p=2 ADR): the multigrid-Krylov solution against SuperLU on the oracle's matrix."""
+    import time
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(65536, tiles=4, seed=1337), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=2)
+    dg.add_data(**PROBLEMS["adr"]["data"])
+    dg.dgfem(solve=True)
+    B, L, info = dg_oracle.assemble(geo, 2, **PROBLEMS["adr"]["data"])
+    t0 = time.time()
+    x = dg_oracle.solve(B, L)
+    print(f"spsolve: {time.time() - t0:.1f} s; ours: {dg.solve_info}")
+    assert util.rel_l2(dg.solution, x) <= util.TOL_SOLUTION, dg.solve_info
+    pr = PROBLEMS["adr"]
+    e = dg.errors(pr["exact"], pr["grad_exact"])
+    eo = dg_oracle.errors(geo, 2, x, pr["exact"], pr["grad_exact"], advection=pr["data"]["advection"],
+                          diffusion=pr["data"]["diffusion"], reaction=pr["data"]["reaction"])
+    for a, b in zip(e, eo):
+        assert abs(a - b) <= util.TOL_ERRORS * abs(b)

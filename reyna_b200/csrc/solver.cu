@@ -9,6 +9,7 @@
 // * CG for the symmetric (pure diffusion / diffusion-reaction) case, BiCGStab otherwise.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace rb {
 
@@ -527,6 +528,42 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     bool done = false, stagnated = false;
     double true_rr = 0.0, prev_true_rr = -1.0;
 
+    // one Krylov iteration (all scalars stay on the device)
+    auto iteration = [&]() -> int {
+        int r_;
+        if (cg) {
+            if ((r_ = s.spmv(s.p, s.v))) return r_;                                   // q = A p
+            k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.p, s.v, s.partial);               // (p,q)
+            if ((r_ = s.reduce(1))) return r_;
+            scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
+            k_cg_xr<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.p, s.r, s.v);
+            if ((r_ = s.precond(s.r, s.z))) return r_;
+            k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, s.partial);               // (r,z), (r,r)
+            if ((r_ = s.reduce(2))) return r_;
+            scal_rho_cg<<<1, 1, 0, st>>>(s.S, s.red);
+            k_cg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.z, s.p);
+        } else {
+            k_bicg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v, s.p);
+            if ((r_ = s.precond(s.p, s.y))) return r_;
+            if ((r_ = s.spmv(s.y, s.v))) return r_;                                   // v = A y
+            k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.rhat, s.v, s.partial);            // (rhat, v)
+            if ((r_ = s.reduce(1))) return r_;
+            scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
+            k_bicg_s<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v);                   // r := s
+            if ((r_ = s.precond(s.r, s.z))) return r_;
+            if ((r_ = s.spmv(s.z, s.t))) return r_;                                   // t = A z
+            k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.r, s.partial);               // (t,s), (t,t)
+            if ((r_ = s.reduce(2))) return r_;
+            scal_omega<<<1, 1, 0, st>>>(s.S, s.red);
+            k_bicg_x<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.y, s.z, s.r, s.t, s.rhat, s.partial);
+            if ((r_ = s.reduce(2))) return r_;
+            scal_rho_bicg<<<1, 1, 0, st>>>(s.S, s.red);
+        }
+        return 0;
+    };
+    // (capturing the whole iteration as one CUDA graph was measured too: no gain over replaying only the multigrid
+    // application, the iteration is bound by device time, not by launches)
+
     // (Re)start from the current x: r = b - A x (true residual), Krylov state reset.  The recurrence residual drifts away
     // from the true one on ill-conditioned systems, so convergence is only ever declared on a true residual.
     for (;;) {
@@ -565,34 +602,7 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
         while (!inner_done && it < opts->max_iter) {
             const int burst = (opts->max_iter - it) < check ? (opts->max_iter - it) : check;
             for (int k = 0; k < burst; ++k) {
-                if (cg) {
-                    if ((rc = s.spmv(s.p, s.v))) return rc;                                  // q = A p
-                    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.p, s.v, s.partial);               // (p,q)
-                    if ((rc = s.reduce(1))) return rc;
-                    scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
-                    k_cg_xr<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.p, s.r, s.v);
-                    if ((rc = s.precond(s.r, s.z))) return rc;
-                    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.r, s.z, s.partial);               // (r,z), (r,r)
-                    if ((rc = s.reduce(2))) return rc;
-                    scal_rho_cg<<<1, 1, 0, st>>>(s.S, s.red);
-                    k_cg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.z, s.p);
-                } else {
-                    k_bicg_p<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v, s.p);
-                    if ((rc = s.precond(s.p, s.y))) return rc;
-                    if ((rc = s.spmv(s.y, s.v))) return rc;                                  // v = A y
-                    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.rhat, s.v, s.partial);            // (rhat, v)
-                    if ((rc = s.reduce(1))) return rc;
-                    scal_alpha<<<1, 1, 0, st>>>(s.S, s.red);
-                    k_bicg_s<<<nb, kVecThreads, 0, st>>>(n, s.S, s.r, s.v);                   // r := s
-                    if ((rc = s.precond(s.r, s.z))) return rc;
-                    if ((rc = s.spmv(s.z, s.t))) return rc;                                  // t = A z
-                    k_dot2<<<nb, kVecThreads, 0, st>>>(n, s.t, s.r, s.partial);               // (t,s), (t,t)
-                    if ((rc = s.reduce(2))) return rc;
-                    scal_omega<<<1, 1, 0, st>>>(s.S, s.red);
-                    k_bicg_x<<<nb, kVecThreads, 0, st>>>(n, s.S, x, s.y, s.z, s.r, s.t, s.rhat, s.partial);
-                    if ((rc = s.reduce(2))) return rc;
-                    scal_rho_bicg<<<1, 1, 0, st>>>(s.S, s.red);
-                }
+                if ((rc = iteration())) return rc;
             }
             RB_LAUNCH_CHECK("krylov burst");
             it += burst;

@@ -52,7 +52,6 @@ struct Dims {
 // plane `pl` of thread `tid`: consecutive threads touch consecutive 16-byte words -> conflict-free
 __device__ __forceinline__ double2* plane(double2* s, int pl, int tid) { return s + (size_t)pl * blockDim.x + tid; }
 
-template <int D>
 __device__ __forceinline__ int gid_of(const AsmArgs& A, int e) { return A.g.elem_gid ? A.g.elem_gid[e] : e; }
 
 // ---- volume ring ------------------------------------------------------------------------------------------------------
@@ -265,7 +264,7 @@ __device__ __forceinline__ void face_pass(const AsmArgs& A, int e, int eg, const
         }
         const bool last_of_group = !has1 || item1 >= 0;     // the next item starts another neighbour
         if (last_of_group) {
-            const int og = gid_of<D>(A, nbr);
+            const int og = gid_of(A, nbr);
             if (DO_DIAG) dslot += (og < eg);
             if (DO_OFF) {
                 const int slot = gi + (og > eg ? 1 : 0);
@@ -305,7 +304,7 @@ __device__ __forceinline__ void element_work(const AsmArgs& A, int e, double2* s
     const int t0 = A.g.tri_off[e], t1 = A.g.tri_off[e + 1];
     const int k0 = A.adj_off[e], k1 = A.adj_off[e + 1];
     const int g0 = A.grp_off[e], g1 = A.grp_off[e + 1];
-    const int eg = gid_of<D>(A, e);
+    const int eg = gid_of(A, e);
     const bool has_c = A.c.vol_c != nullptr, has_f = A.c.vol_f != nullptr;
     const size_t T = (size_t)A.g.n_tri;
 

@@ -6,8 +6,9 @@ The reference is a single-process program; this module 
 * the rank's block rows in LOCAL column numbering (owned coefficients followed by ghost coefficients),
 * a halo exchange of ghost-element coefficients before every SpMV and an all-reduce of every dot product, both issued
   from inside the library over NCCL on the solver's stream (``csrc/dist.cu``),
-* the multigrid hierarchy built per rank on its own diagonal block (additive Schwarz across ranks, no coarse-level
-  communication).
+* the multigrid hierarchy distributed as well: fine and P1 levels are partitioned (two 3-coefficient halo exchanges per
+  application), the piecewise-constant chain is GLOBAL and replicated (its rows are all-gathered once per solve, its
+  right-hand side once per application), so the iteration counts do not grow with the number of GPUs.
 
 ``torch.distributed`` (any backend) is only used to hand out the NCCL unique id and to gather the solution.
 """

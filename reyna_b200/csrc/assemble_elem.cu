@@ -154,7 +154,12 @@ __device__ __forceinline__ void face_point(const AsmArgs& A, const FaceGeo& g, d
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         Pr[j] = sgn * phi[j];
-        if (DIFF) Qr[j] = -0.5 * (atn0 * gx[j] + atn1 * gy[j]);
+        Qr[j] = 0.0;
+        if (DIFF) {
+            if (gx_nz<P>(j) && gy_nz<P>(j)) Qr[j] = -0.5 * (atn0 * gx[j] + atn1 * gy[j]);
+            else if (gx_nz<P>(j)) Qr[j] = -0.5 * (atn0 * gx[j]);
+            else if (gy_nz<P>(j)) Qr[j] = -0.5 * (atn1 * gy[j]);
+        }
     }
     const double Ws = W * sgn;
     if (DO_DIAG) {
@@ -163,12 +168,13 @@ __device__ __forceinline__ void face_point(const AsmArgs& A, const FaceGeo& g, d
             const int i = I0 + ii;
             const double Vc = Ws * phi[i];
             double Uc = sg * Vc;
-            if (DIFF) Uc = fma(hw0, gx[i], fma(hw1, gy[i], Uc));
+            if (DIFF && gy_nz<P>(i)) Uc = fma(hw1, gy[i], Uc);
+            if (DIFF && gx_nz<P>(i)) Uc = fma(hw0, gx[i], Uc);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 double v = dacc[j * CI + ii];
                 v = fma(Pr[j], Uc, v);
-                if (DIFF) v = fma(Qr[j], Vc, v);
+                if (DIFF && (gx_nz<P>(j) || gy_nz<P>(j))) v = fma(Qr[j], Vc, v);
                 dacc[j * CI + ii] = v;
             }
         }
@@ -180,12 +186,13 @@ __device__ __forceinline__ void face_point(const AsmArgs& A, const FaceGeo& g, d
             const int i = I0 + ii;
             const double Vc = -Ws * phi[i];
             double Uc = sg * Vc;
-            if (DIFF) Uc = fma(hw0, gx[i], fma(hw1, gy[i], Uc));
+            if (DIFF && gy_nz<P>(i)) Uc = fma(hw1, gy[i], Uc);
+            if (DIFF && gx_nz<P>(i)) Uc = fma(hw0, gx[i], Uc);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 double v = oacc[j * CI + ii];
                 v = fma(Pr[j], Uc, v);
-                if (DIFF) v = fma(Qr[j], Vc, v);
+                if (DIFF && (gx_nz<P>(j) || gy_nz<P>(j))) v = fma(Qr[j], Vc, v);
                 oacc[j * CI + ii] = v;
             }
         }
@@ -385,19 +392,29 @@ __device__ __forceinline__ void element_work(const AsmArgs& A, int e, double2* s
 #pragma unroll
                 for (int ii = 0; ii < CI; ++ii) {
                     const int i = I0 + ii;
+                    const bool nzx = gx_nz<P>(i), nzy = gy_nz<P>(i);     // compile-time after unrolling
                     double u0 = 0, u1 = 0;
                     if (DIFF) {
-                        u0 = fma(gx[i], a00, gy[i] * a10);
-                        u1 = fma(gx[i], a01, gy[i] * a11);
+                        if (nzx && nzy) {
+                            u0 = fma(gx[i], a00, gy[i] * a10);
+                            u1 = fma(gx[i], a01, gy[i] * a11);
+                        } else if (nzx) {
+                            u0 = gx[i] * a00;
+                            u1 = gx[i] * a01;
+                        } else if (nzy) {
+                            u0 = gy[i] * a10;
+                            u1 = gy[i] * a11;
+                        }
                     }
                     double si = cq * phi[i];
-                    if (ADV) si = fma(b0, gx[i], fma(b1, gy[i], si));
+                    if (ADV && nzy) si = fma(b1, gy[i], si);
+                    if (ADV && nzx) si = fma(b0, gx[i], si);
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
                         double v = acc[j * CI + ii];
-                        if (DIFF) {
-                            v = fma(u0, gx[j], v);
-                            v = fma(u1, gy[j], v);
+                        if (DIFF && (nzx || nzy)) {
+                            if (gx_nz<P>(j)) v = fma(u0, gx[j], v);
+                            if (gy_nz<P>(j)) v = fma(u1, gy[j], v);
                         }
                         v = fma(si, phi[j], v);
                         acc[j * CI + ii] = v;

@@ -103,7 +103,26 @@ struct BasisDim {
     static constexpr int D = (P + 1) * (P + 2) / 2;
 };
 
+// (i,j) of basis index k, branch-free so that it folds to a constant inside unrolled loops (rows start at 0, P+1, 2P+1, 3P).
+template <int P>
+__host__ __device__ constexpr int basis_i(int k) {
+    static_assert(P <= 3, "basis_i: row starts are written out for P <= 3");
+    return (k >= P + 1) + (k >= 2 * P + 1) + (k >= 3 * P);
+}
+template <int P>
+__host__ __device__ constexpr int basis_j(int k) {
+    const int i = basis_i<P>(k);
+    return k - (i * (P + 1) - i * (i - 1) / 2);
+}
+// d/dx phi_k vanishes identically for i = 0 and d/dy phi_k for j = 0 (P_0' = 0, assembly_aux.py:112-133 multiplies by that
+// exact zero): the kernels skip those products and the FMAs that would add their exact zeros.
+template <int P>
+__host__ __device__ constexpr bool gx_nz(int k) { return basis_i<P>(k) > 0; }
+template <int P>
+__host__ __device__ constexpr bool gy_nz(int k) { return basis_j<P>(k) > 0; }
+
 // phi[k], and (when GRAD) d/dx, d/dy of the D basis functions of the element with box `bx` at the point (x,y).
+// gx[k] / gy[k] of the identically-zero entries are set to a literal 0 (dead when the caller honours gx_nz / gy_nz).
 template <int P, bool GRAD>
 __device__ __forceinline__ void eval_basis(double x, double y, const ElemBox& bx, const LegConst& lc,
                                            double (&phi)[BasisDim<P>::D], double (&gx)[BasisDim<P>::D],
@@ -118,8 +137,8 @@ __device__ __forceinline__ void eval_basis(double x, double y, const ElemBox& bx
         for (int j = 0; j <= P - i; ++j) {
             phi[k] = vx[i] * vy[j];
             if (GRAD) {
-                gx[k] = dx[i] * vy[j];
-                gy[k] = vx[i] * dy[j];
+                gx[k] = i > 0 ? dx[i] * vy[j] : 0.0;
+                gy[k] = j > 0 ? vx[i] * dy[j] : 0.0;
             }
             ++k;
         }

@@ -191,7 +191,7 @@ def run_reference(args, rank: int) -> None:
         "note": "reyna is pure Python (no C sources to compile into oracle/_ref); its own loops run at ~5e3 DoF/s on one "
                 "core (SURVEY.md section 6), the vectorised oracle port timed here is ~8x faster per core",
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -439,12 +439,36 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "value": ndof / times[0], "unit": "DoF/s", "cores": cores, "kind": "port",
             "sample": f"oracle/dg_oracle.py (numpy port of reyna's dgfem(solve=False)) assembling one "
                       f"{args.baseline_sample}-element partition of the workload, {times[0]:.1f} s, 1 process"}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout() -> None:
+    """Keep stdout for the ONE JSON line: everything else written to fd 1 from here on (NCCL's version banner, library
+    prints of child code) is routed to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main() -> None:
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

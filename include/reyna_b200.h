@@ -184,6 +184,10 @@ typedef struct {
     int32_t nu;                /* damped-Jacobi sweeps before and after every coarse correction (default 3)   */
     double  omega;             /* Jacobi damping (default 0.7)                                                */
     double  alpha;             /* scaling of the aggregation coarse corrections (default 1.8)                 */
+    const double *elem_bbox;   /* DEVICE [n_elem][4] (xmin,xmax,ymin,ymax) or NULL.  When given (single-GPU hierarchy),
+                                * the levels below P1 are AGGLOMERATED P1 spaces: groups of 4 consecutive elements,
+                                * linear polynomials on the bounding box of the group, 3 x 3 block Jacobi smoothing --
+                                * instead of the piecewise-constant aggregation chain                          */
 } rb_mg_opts;
 /* Distributed hierarchy (dd != NULL): the fine and P1 levels are the rank's rows in LOCAL column numbering (halo exchange
  * through dd->dist), the piecewise-constant level is GLOBAL: the caller gathers every rank's P0 rows (global element

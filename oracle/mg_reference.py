@@ -77,3 +77,84 @@ class CoarseCorrection:
 
     def level_sizes(self):
         return [L["A"].shape[0] for L in self.levels]
+
+
+class AgglomeratedP1:
+    """z = R1^T V(R1 r) (p >= 2) / z = alpha P V(P^T r) (p = 1): the agglomerated-P1 chain of multigrid.cu (rb_mg_opts.elem_bbox
+    given).  Every level keeps the modes (0,0), (0,1), (1,0) per (agglomerated) element; an aggregate is 4 consecutive
+    elements and its basis the scaled Legendre polynomials of degree <= 1 on the bounding box of the group."""
+
+    C0, C1 = 1.0 / np.sqrt(2.0), np.sqrt(1.5)
+
+    def __init__(self, B: sp.csr_matrix, p: int, bbox: np.ndarray, nu: int = 2, omega: float = 0.8, alpha: float = 2.2,
+                 dense_max: int = 256):
+        d = (p + 1) * (p + 2) // 2
+        N = B.shape[0]
+        E = N // d
+        self.nu, self.omega, self.alpha, self.p = nu, omega, alpha, p
+        self.has_p1 = d > 3
+        if self.has_p1:
+            sel = np.array([0, 1, p + 1])
+            self.R1 = sp.csr_matrix((np.ones(3 * E), ((np.arange(E)[:, None] * d + sel[None]).ravel(), np.arange(3 * E))),
+                                    shape=(N, 3 * E))
+            A = (self.R1.T @ B @ self.R1).tocsr()
+        else:
+            A = B.tocsr()
+        bb = np.asarray(bbox, dtype=float).reshape(-1, 4)
+        self.levels = []
+        while True:
+            n = A.shape[0]
+            if n <= dense_max:
+                self.levels.append(dict(A=A, inv=np.linalg.inv(A.toarray())))
+                break
+            P, bb_c = self._prolongation(bb)
+            self.levels.append(dict(A=A, M=block_inverse(A, 3), P=P))
+            A = (P.T @ A @ P).tocsr()
+            bb = bb_c
+
+    @classmethod
+    def _coefs(cls, bb):
+        hx, hy = 0.5 * (bb[:, 1] - bb[:, 0]), 0.5 * (bb[:, 3] - bb[:, 2])
+        mx, my = 0.5 * (bb[:, 1] + bb[:, 0]), 0.5 * (bb[:, 3] + bb[:, 2])
+        r = 1.0 / np.sqrt(hx * hy)
+        return mx, my, cls.C0 * cls.C0 * r, cls.C0 * cls.C1 * r / hx, cls.C0 * cls.C1 * r / hy
+
+    @classmethod
+    def _prolongation(cls, bb_f):
+        n = bb_f.shape[0]
+        nc = (n + 3) // 4
+        gid = np.arange(n) // 4
+        starts = np.arange(0, n, 4)
+        bb_c = np.stack([np.minimum.reduceat(bb_f[:, 0], starts), np.maximum.reduceat(bb_f[:, 1], starts),
+                         np.minimum.reduceat(bb_f[:, 2], starts), np.maximum.reduceat(bb_f[:, 3], starts)], axis=1)
+        mxf, myf, k00f, kxf, kyf = cls._coefs(bb_f)
+        mxc, myc, k00c, kxc, kyc = [a[gid] for a in cls._coefs(bb_c)]
+        f = np.arange(n)
+        rows = np.concatenate([3 * f, 3 * f + 1, 3 * f, 3 * f + 2, 3 * f])
+        cols = np.concatenate([3 * gid, 3 * gid + 1, 3 * gid + 1, 3 * gid + 2, 3 * gid + 2])
+        vals = np.concatenate([k00c / k00f, kyc / kyf, kyc * (myf - myc) / k00f, kxc / kxf, kxc * (mxf - mxc) / k00f])
+        return sp.csr_matrix((vals, (rows, cols)), shape=(3 * n, 3 * nc)), bb_c
+
+    def vcycle(self, k: int, b: np.ndarray) -> np.ndarray:
+        L = self.levels[k]
+        if "inv" in L:
+            return L["inv"] @ b
+        A, M, P = L["A"], L["M"], L["P"]
+        x = self.omega * (M @ b)
+        for _ in range(1, self.nu):
+            x = x + self.omega * (M @ (b - A @ x))
+        x = x + self.alpha * (P @ self.vcycle(k + 1, P.T @ (b - A @ x)))
+        for _ in range(self.nu):
+            x = x + self.omega * (M @ (b - A @ x))
+        return x
+
+    def apply(self, r: np.ndarray) -> np.ndarray:
+        if self.has_p1:
+            return self.R1 @ self.vcycle(0, self.R1.T @ r)
+        L0 = self.levels[0]
+        if "inv" in L0:
+            return L0["inv"] @ r
+        return self.alpha * (L0["P"] @ self.vcycle(1, L0["P"].T @ r))
+
+    def level_sizes(self):
+        return [L["A"].shape[0] for L in self.levels]

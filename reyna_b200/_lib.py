@@ -55,7 +55,7 @@ class RbStructure(C.Structure):
 
 
 class RbMgOpts(C.Structure):
-    _fields_ = [("nu", C.c_int32), ("omega", C.c_double), ("alpha", C.c_double)]
+    _fields_ = [("nu", C.c_int32), ("omega", C.c_double), ("alpha", C.c_double), ("elem_bbox", C.c_void_p)]
 
 
 class RbMgDist(C.Structure):

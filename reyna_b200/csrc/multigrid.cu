@@ -13,6 +13,9 @@
 //   z += P1^T V1(P1 r)                             V1: block-Jacobi sweep, P0 correction, block-Jacobi sweep  (3 x 3 blocks)
 //   P0 correction: V-cycle over the aggregation levels with `nu` damped-Jacobi sweeps, coarse corrections scaled by
 //   `alpha` (unsmoothed aggregation under-corrects), exact dense solve at the coarsest level.
+// With element bounding boxes (rb_mg_opts.elem_bbox) the levels below P1 are AGGLOMERATED P1 spaces instead (groups of 4
+// consecutive elements, linear polynomials on the bounding box of the group, 3 x 3 block Jacobi, V(nu,nu)): linear functions
+// are represented on every level, which the piecewise-constant chain cannot do (2-3 times fewer Krylov iterations).
 // Iteration counts become mesh independent (p = 2: 250 ... 490 BiCGStab / 400 ... 730 CG iterations down to the rounding floor
 // of the true residual between 65k and 1M elements; block Jacobi alone: 21 500 / 44 050 at 65k / 262k).
 #include "common.cuh"
@@ -33,6 +36,11 @@ struct MgLevel {
     double* data = nullptr;
     double* dinv = nullptr;
     double *b = nullptr, *x = nullptr, *xt = nullptr;   // right-hand side, iterate, ping-pong iterate
+    // agglomerated-P1 chain (3 x 3 blocks; n = 3 * n_blk scalar rows)
+    int n_blk = 0;
+    double* minv = nullptr;      // [n_blk][3][3]  omega * inverse of the diagonal block
+    double* bbox = nullptr;      // [n_blk][4]     bounding box of the (agglomerated) element
+    double* tr = nullptr;        // [n_blk][8]     its P1 basis expressed in the basis of its aggregate (next level)
 };
 
 }  // namespace rb
@@ -61,6 +69,9 @@ struct rb_mg {
     int n_ghost_elem = 0, lo_elem = 0;
     std::vector<int32_t> bounds;
     std::vector<void*> owned;
+    // agglomerated-P1 chain (rb_mg_opts.elem_bbox given): blev[0] is the P1 level itself
+    int agg_p1 = 0, nblev = 0;
+    rb::MgLevel blev[rb::kMaxLevels];
 };
 
 namespace rb {
@@ -379,6 +390,169 @@ __global__ void mg_pad_add(int n_elem, int d, int dc, int s0, int s1, int s2, co
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// agglomerated-P1 chain: every level keeps the three modes (0,0), (0,1), (1,0) per (agglomerated) element.  An aggregate
+// is 4 consecutive elements, its basis the scaled Legendre polynomials of degree <= 1 on the bounding box of the group
+// (the same construction as the element basis, assembly_aux.py:32-66), so that P1 functions are represented exactly
+// on every level.  With k00 = c0^2 / sqrt(hx hy), ky = c0 c1 / (sqrt(hx hy) hy), kx likewise:
+//   Phi_00 = (K00/k00) phi_00,   Phi_01 = (Ky/ky) phi_01 + Ky (my - My)/k00 phi_00,   Phi_10 = (Kx/kx) phi_10 + ... phi_00
+// (capitals: aggregate, lower case: member element).  tr = {s00, syy, sy0, sxx, sx0}.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void mgb_coarsen_bbox(int nc, int n, const double* __restrict__ bf, double* __restrict__ bc) {
+    for (int G = blockIdx.x * blockDim.x + threadIdx.x; G < nc; G += gridDim.x * blockDim.x) {
+        double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+        for (int e = 4 * G; e < 4 * G + 4 && e < n; ++e) {
+            x0 = fmin(x0, bf[4 * (size_t)e]); x1 = fmax(x1, bf[4 * (size_t)e + 1]);
+            y0 = fmin(y0, bf[4 * (size_t)e + 2]); y1 = fmax(y1, bf[4 * (size_t)e + 3]);
+        }
+        bc[4 * (size_t)G] = x0; bc[4 * (size_t)G + 1] = x1; bc[4 * (size_t)G + 2] = y0; bc[4 * (size_t)G + 3] = y1;
+    }
+}
+
+struct BoxK { double mx, my, k00, kx, ky; };
+__device__ __forceinline__ BoxK box_k(const double* __restrict__ b) {
+    const double hx = 0.5 * (b[1] - b[0]), hy = 0.5 * (b[3] - b[2]);
+    BoxK k;
+    k.mx = 0.5 * (b[1] + b[0]); k.my = 0.5 * (b[3] + b[2]);
+    const double r = rsqrt(hx * hy);
+    k.k00 = 0.5 * r;                                   // c0^2,  c0 = 1/sqrt(2)
+    const double c01 = 0.8660254037844386 * r;         // c0 c1, c1 = sqrt(3/2)
+    k.kx = c01 / hx; k.ky = c01 / hy;
+    return k;
+}
+
+__global__ void mgb_transfer(int n, const double* __restrict__ bf, const double* __restrict__ bc, double* __restrict__ tr) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const BoxK f = box_k(bf + 4 * (size_t)e), c = box_k(bc + 4 * (size_t)(e >> 2));
+        double* t = tr + 8 * (size_t)e;
+        t[0] = c.k00 / f.k00;
+        t[1] = c.ky / f.ky; t[2] = c.ky * (f.my - c.my) / f.k00;
+        t[3] = c.kx / f.kx; t[4] = c.kx * (f.mx - c.mx) / f.k00;
+        t[5] = t[6] = t[7] = 0.0;
+    }
+}
+
+// M (3 x 3, row-major) <- Pe^T A Pf, with P = [[s00, sy0, sx0], [0, syy, 0], [0, 0, sxx]] (rows: element modes)
+__device__ __forceinline__ void mgb_transform(const double* __restrict__ te, const double* __restrict__ tf, const double (&a)[9],
+                                              double (&m)[9]) {
+    const double pe[9] = {te[0], te[2], te[4], 0.0, te[1], 0.0, 0.0, 0.0, te[3]};
+    const double pf[9] = {tf[0], tf[2], tf[4], 0.0, tf[1], 0.0, 0.0, 0.0, tf[3]};
+    double ap[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ap[i * 3 + j] = a[i * 3 + 0] * pf[0 * 3 + j] + a[i * 3 + 1] * pf[1 * 3 + j] + a[i * 3 + 2] * pf[2 * 3 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) m[i * 3 + j] = pe[0 * 3 + i] * ap[0 * 3 + j] + pe[1 * 3 + i] * ap[1 * 3 + j] + pe[2 * 3 + i] * ap[2 * 3 + j];
+}
+
+// Galerkin coarse operator of one agglomeration step, one thread per coarse block row.  The fine matrix is a scalar CSR
+// matrix with complete 3 x 3 blocks (block columns ascending); FILL == false counts the coarse blocks per row.
+template <bool FILL>
+__global__ void mgb_aggregate(int nc, int n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                              const double* __restrict__ data, const double* __restrict__ tr,
+                              int32_t* __restrict__ blk_cnt_or_off, int32_t* __restrict__ c_indptr,
+                              int32_t* __restrict__ c_indices, double* __restrict__ c_data) {
+    for (int G = blockIdx.x * blockDim.x + threadIdx.x; G < nc; G += gridDim.x * blockDim.x) {
+        int pos[4], end[4], lo[4];
+        const int e0 = 4 * G;
+        const int nr = n - e0 < 4 ? n - e0 : 4;
+        for (int k = 0; k < nr; ++k) {
+            lo[k] = indptr[3 * (e0 + k)];
+            pos[k] = 0;
+            end[k] = (indptr[3 * (e0 + k) + 1] - lo[k]) / 3;       // blocks of fine block row e0 + k
+            while (pos[k] < end[k] && indices[lo[k] + 3 * pos[k]] / 3 >= n) ++pos[k];   // ghost couplings are skipped
+        }
+        int count = 0;
+        if (!FILL) {
+            for (;;) {
+                int hmin = 0x7fffffff;
+                for (int k = 0; k < nr; ++k)
+                    if (pos[k] < end[k]) { const int h = indices[lo[k] + 3 * pos[k]] / 12; hmin = h < hmin ? h : hmin; }
+                if (hmin == 0x7fffffff) break;
+                for (int k = 0; k < nr; ++k)
+                    while (pos[k] < end[k] && indices[lo[k] + 3 * pos[k]] / 12 == hmin) {
+                        ++pos[k];
+                        while (pos[k] < end[k] && indices[lo[k] + 3 * pos[k]] / 3 >= n) ++pos[k];
+                    }
+                ++count;
+            }
+            blk_cnt_or_off[G] = count;
+            continue;
+        }
+        const int b0 = blk_cnt_or_off[G], nbG = blk_cnt_or_off[G + 1] - b0;
+        const int row0 = 9 * b0;                                 // scalar row 3G + i starts at row0 + i * 3 * nbG
+        c_indptr[3 * G] = row0; c_indptr[3 * G + 1] = row0 + 3 * nbG; c_indptr[3 * G + 2] = row0 + 6 * nbG;
+        if (G == nc - 1) c_indptr[3 * nc] = row0 + 9 * nbG;
+        for (;;) {
+            int hmin = 0x7fffffff;
+            for (int k = 0; k < nr; ++k)
+                if (pos[k] < end[k]) { const int h = indices[lo[k] + 3 * pos[k]] / 12; hmin = h < hmin ? h : hmin; }
+            if (hmin == 0x7fffffff) break;
+            double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < nr; ++k) {                       // fixed order: rows ascending, blocks ascending
+                const int e = e0 + k;
+                const int len = indptr[3 * e + 1] - lo[k];       // scalar row length of the fine block row
+                while (pos[k] < end[k] && indices[lo[k] + 3 * pos[k]] / 12 == hmin) {
+                    const int f = indices[lo[k] + 3 * pos[k]] / 3;
+                    double a[9], m[9];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) a[i * 3 + j] = data[lo[k] + i * len + 3 * pos[k] + j];
+                    mgb_transform(tr + 8 * (size_t)e, tr + 8 * (size_t)f, a, m);
+#pragma unroll
+                    for (int v = 0; v < 9; ++v) acc[v] += m[v];
+                    ++pos[k];
+                    while (pos[k] < end[k] && indices[lo[k] + 3 * pos[k]] / 3 >= n) ++pos[k];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    c_indices[row0 + i * 3 * nbG + 3 * count + j] = 3 * hmin + j;
+                    c_data[row0 + i * 3 * nbG + 3 * count + j] = acc[i * 3 + j];
+                }
+            ++count;
+        }
+    }
+}
+
+__global__ void mgb_scale(int64_t n, double s, double* __restrict__ v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] *= s;
+}
+
+// bc[G] = sum over the members e of G of Pe^T t[e]   (fixed member order: deterministic)
+__global__ void mgb_restrict(int nc, int n, const double* __restrict__ tr, const double* __restrict__ t, double* __restrict__ bc) {
+    for (int G = blockIdx.x * blockDim.x + threadIdx.x; G < nc; G += gridDim.x * blockDim.x) {
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        for (int e = 4 * G; e < 4 * G + 4 && e < n; ++e) {
+            const double* q = tr + 8 * (size_t)e;
+            const double t0 = t[3 * (size_t)e], t1 = t[3 * (size_t)e + 1], t2 = t[3 * (size_t)e + 2];
+            r0 = fma(q[0], t0, r0);
+            r1 += fma(q[2], t0, q[1] * t1);
+            r2 += fma(q[4], t0, q[3] * t2);
+        }
+        bc[3 * (size_t)G] = r0; bc[3 * (size_t)G + 1] = r1; bc[3 * (size_t)G + 2] = r2;
+    }
+}
+
+// x[e] += alpha * Pe xc[G]
+__global__ void mgb_prolong_add(int n, double alpha, const double* __restrict__ tr, const double* __restrict__ xc,
+                                double* __restrict__ x) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const double* q = tr + 8 * (size_t)e;
+        const double* c = xc + 3 * (size_t)(e >> 2);
+        x[3 * (size_t)e] += alpha * (q[0] * c[0] + q[2] * c[1] + q[4] * c[2]);
+        x[3 * (size_t)e + 1] += alpha * (q[1] * c[1]);
+        x[3 * (size_t)e + 2] += alpha * (q[3] * c[2]);
+    }
+}
+
 int launch_block_columns(int n_block_rows, int d, const int32_t* indptr, const int32_t* indices, int32_t* bcol,
                          cudaStream_t st);   // solver.cu
 void block_jacobi_setup_launch(int n_blocks, int d, const int32_t* indptr, const int32_t* indices, const double* data,
@@ -419,6 +593,45 @@ static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     return 0;
 }
 
+
+// V-cycle on the agglomerated-P1 chain, level k: blev[k].b holds the right-hand side, the result is left in blev[k].x.
+// Smoother: nu sweeps of 3 x 3 block Jacobi (the damping is folded into minv), coarse corrections scaled by alpha.
+static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
+    MgLevel& L = mg->blev[k];
+    if (k == mg->nblev - 1) {
+        mg_dense_apply<<<(L.n + 31) / 32, 256, 0, st>>>(L.n, mg->dense_inv, L.b, L.x);
+        RB_LAUNCH_CHECK("mg_dense_apply");
+        return 0;
+    }
+    const int g = mg_grid(L.n);
+    const bool top_blocked = (k == 0 && mg->has_p1);             // the P1 level shares the fine level's block columns
+    auto residual = [&]() {
+        if (top_blocked)
+            mg_residual_blocked3<8><<<mg_grid((int64_t)L.n * 8), kMgThreads, 0, st>>>(L.n, L.n, L.indptr, mg->bcol, L.data, L.b, L.x, L.xt);
+        else
+            mg_residual<8><<<mg_grid((int64_t)L.n * 8), kMgThreads, 0, st>>>(L.n, L.n, L.indptr, L.indices, L.data, L.b, L.x, L.xt);
+    };
+    mg_block_apply<false><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.b, L.x);
+    for (int s = 1; s < mg->nu; ++s) {
+        residual();
+        mg_block_apply<true><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.xt, L.x);
+    }
+    RB_LAUNCH_CHECK("mgb pre-smoothing");
+    MgLevel& C = mg->blev[k + 1];
+    residual();
+    mgb_restrict<<<mg_grid(C.n_blk), kMgThreads, 0, st>>>(C.n_blk, L.n_blk, L.tr, L.xt, C.b);
+    RB_LAUNCH_CHECK("mgb_restrict");
+    int rc = mgb_vcycle(mg, k + 1, st);
+    if (rc) return rc;
+    mgb_prolong_add<<<mg_grid(L.n_blk), kMgThreads, 0, st>>>(L.n_blk, mg->alpha, L.tr, C.x, L.x);
+    for (int s = 0; s < mg->nu; ++s) {
+        residual();
+        mg_block_apply<true><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.xt, L.x);
+    }
+    RB_LAUNCH_CHECK("mgb post-smoothing");
+    return 0;
+}
+
 int dist_halo_d(rb_dist* h, double* x, int d, cudaStream_t st);                                           // dist.cu
 int dist_allgather_rows(rb_dist* h, const double* local, double* global, const int32_t* bounds, cudaStream_t st);
 
@@ -432,6 +645,35 @@ __global__ void mg_copy_slice(int n, const double* __restrict__ in, int offset, 
 // z += (coarse-space correction of r); r, z fine-level vectors (owned part)
 int mg_apply_add(rb_mg* mg, const double* r, double* z, cudaStream_t st) {
     const int E = mg->n_elem, d = mg->d;
+    if (mg->agg_p1) {
+        int rc;
+        MgLevel& B0 = mg->blev[0];
+        if (mg->has_p1) {
+            // z += R1^T V(R1 r): V-cycle over the agglomerated-P1 chain starting on the P1 level
+            const int s0 = mg->sel1[0], s1 = mg->sel1[1], s2 = mg->sel1[2];
+            mg_select<<<mg_grid(3 * E), kMgThreads, 0, st>>>(E, d, 3, s0, s1, s2, r, B0.b);
+            RB_LAUNCH_CHECK("mg_select");
+            if ((rc = mgb_vcycle(mg, 0, st))) return rc;
+            mg_pad_add<<<mg_grid(3 * E), kMgThreads, 0, st>>>(E, d, 3, s0, s1, s2, B0.x, z);
+            RB_LAUNCH_CHECK("mg_pad_add");
+        } else {
+            // p = 1: the fine level is the P1 level and block Jacobi on it is the (additive) smoother of the caller;
+            // z += alpha P V(P^T r) with the chain starting on the first agglomerated level
+            if (mg->nblev == 1) {          // tiny mesh: the fine level itself is solved densely
+                mg_dense_apply<<<(B0.n + 31) / 32, 256, 0, st>>>(B0.n, mg->dense_inv, r, B0.x);
+                mg_pad_add<<<mg_grid(B0.n), kMgThreads, 0, st>>>(E, 3, 3, 0, 1, 2, B0.x, z);
+                RB_LAUNCH_CHECK("mg dense fine level");
+                return 0;
+            }
+            MgLevel& B1 = mg->blev[1];
+            mgb_restrict<<<mg_grid(B1.n_blk), kMgThreads, 0, st>>>(B1.n_blk, B0.n_blk, B0.tr, r, B1.b);
+            RB_LAUNCH_CHECK("mgb_restrict");
+            if ((rc = mgb_vcycle(mg, 1, st))) return rc;
+            mgb_prolong_add<<<mg_grid(B0.n_blk), kMgThreads, 0, st>>>(B0.n_blk, mg->alpha, B0.tr, B1.x, z);
+            RB_LAUNCH_CHECK("mgb_prolong_add");
+        }
+        return 0;
+    }
     MgLevel& L0 = mg->lev[0];
     const bool dist = mg->dist != nullptr;
     // in distributed mode the local P0 right-hand side / correction live in the ping-pong vector of level 0's tail
@@ -563,6 +805,73 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
                                                            L0.data);
     }
     if (cudaGetLastError() != cudaSuccess) { set_error("reyna_b200_mg_create: mode extraction failed"); return fail(RB_E_ARG); }
+
+    // ---- agglomerated-P1 chain (single-GPU hierarchy with element bounding boxes) ----------------------------------------
+    if (!dd && opts && opts->elem_bbox && d >= 3) {
+        mg->agg_p1 = 1;
+        MgLevel& B0 = mg->blev[0];
+        B0.n_blk = E; B0.n = 3 * E;
+        if (mg->has_p1) {
+            B0.indptr = mg->p1_indptr; B0.indices = mg->p1_indices; B0.data = mg->p1_data;
+            B0.minv = mg->p1_minv; B0.b = mg->p1_r; B0.x = mg->p1_x; B0.xt = mg->p1_t;
+            mgb_scale<<<mg_grid((int64_t)9 * E), kMgThreads, 0, st>>>((int64_t)9 * E, mg->omega, B0.minv);
+        } else {
+            B0.indptr = const_cast<int32_t*>(indptr); B0.indices = const_cast<int32_t*>(indices); B0.data = const_cast<double*>(data);
+            if ((rc = dev_alloc(mg, (void**)&B0.x, sizeof(double) * (size_t)B0.n))) return fail(rc);
+        }
+        B0.nnz = nblocks * 9;
+        B0.bbox = const_cast<double*>(opts->elem_bbox);
+        int32_t* scratch = nullptr;
+        if ((rc = dev_alloc(mg, (void**)&scratch, sizeof(int32_t) * (scan_scratch_ints((int64_t)E + 2) + 4)))) return fail(rc);
+        int* sing = nullptr;
+        if ((rc = dev_alloc(mg, (void**)&sing, sizeof(int)))) return fail(rc);
+        cudaMemsetAsync(sing, 0, sizeof(int), st);
+        int k = 0;
+        while (mg->blev[k].n > kDenseMax && k < kMaxLevels - 1) {
+            MgLevel& L = mg->blev[k];
+            MgLevel& C = mg->blev[k + 1];
+            C.n_blk = (L.n_blk + 3) / 4; C.n = 3 * C.n_blk;
+            if ((rc = dev_alloc(mg, (void**)&C.bbox, sizeof(double) * 4 * (size_t)C.n_blk))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&L.tr, sizeof(double) * 8 * (size_t)L.n_blk))) return fail(rc);
+            mgb_coarsen_bbox<<<mg_grid(C.n_blk), kMgThreads, 0, st>>>(C.n_blk, L.n_blk, L.bbox, C.bbox);
+            mgb_transfer<<<mg_grid(L.n_blk), kMgThreads, 0, st>>>(L.n_blk, L.bbox, C.bbox, L.tr);
+            int32_t* boff = nullptr;
+            if ((rc = dev_alloc(mg, (void**)&boff, sizeof(int32_t) * ((size_t)C.n_blk + 1)))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&C.indptr, sizeof(int32_t) * ((size_t)C.n + 1)))) return fail(rc);
+            mgb_aggregate<false><<<mg_grid(C.n_blk), kMgThreads, 0, st>>>(C.n_blk, L.n_blk, L.indptr, L.indices, L.data, L.tr, boff,
+                                                                      nullptr, nullptr, nullptr);
+            RB_CUDA(cudaMemsetAsync(boff + C.n_blk, 0, sizeof(int32_t), st));
+            if ((rc = exclusive_scan_i32(boff, boff, (int64_t)C.n_blk + 1, scratch, nullptr, st))) return fail(rc);
+            int32_t tot = 0;
+            RB_CUDA(cudaMemcpyAsync(&tot, boff + C.n_blk, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            RB_CUDA(cudaStreamSynchronize(st));
+            C.nnz = (int64_t)tot * 9;
+            if ((rc = dev_alloc(mg, (void**)&C.indices, sizeof(int32_t) * (size_t)C.nnz))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&C.data, sizeof(double) * (size_t)C.nnz))) return fail(rc);
+            mgb_aggregate<true><<<mg_grid(C.n_blk), kMgThreads, 0, st>>>(C.n_blk, L.n_blk, L.indptr, L.indices, L.data, L.tr, boff,
+                                                                     C.indptr, C.indices, C.data);
+            if ((rc = dev_alloc(mg, (void**)&C.minv, sizeof(double) * 9 * (size_t)C.n_blk))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&C.b, sizeof(double) * (size_t)C.n))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&C.x, sizeof(double) * (size_t)C.n))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&C.xt, sizeof(double) * (size_t)C.n))) return fail(rc);
+            block_jacobi_setup_launch(C.n_blk, 3, C.indptr, C.indices, C.data, C.minv, sing, st);
+            mgb_scale<<<mg_grid((int64_t)9 * C.n_blk), kMgThreads, 0, st>>>((int64_t)9 * C.n_blk, mg->omega, C.minv);
+            if (cudaGetLastError() != cudaSuccess) { set_error("reyna_b200_mg_create: agglomeration failed"); return fail(RB_E_ARG); }
+            ++k;
+        }
+        mg->nblev = k + 1;
+        mg->nlev = mg->nblev;
+        for (int q = 0; q < mg->nblev; ++q) { mg->lev[q].n = mg->blev[q].n; mg->lev[q].nnz = mg->blev[q].nnz; }   // reyna_b200_mg_info
+        MgLevel& Lc = mg->blev[mg->nblev - 1];
+        double* scratch_a = nullptr;
+        if ((rc = dev_alloc(mg, (void**)&scratch_a, sizeof(double) * (size_t)Lc.n * Lc.n))) return fail(rc);
+        if ((rc = dev_alloc(mg, (void**)&mg->dense_inv, sizeof(double) * (size_t)Lc.n * Lc.n))) return fail(rc);
+        mg_dense_inverse<<<1, 256, 0, st>>>(Lc.n, Lc.indptr, Lc.indices, Lc.data, scratch_a, mg->dense_inv);
+        if (cudaGetLastError() != cudaSuccess) { set_error("reyna_b200_mg_create: dense inverse failed"); return fail(RB_E_ARG); }
+        RB_CUDA(cudaStreamSynchronize(st));
+        *out = mg;
+        return 0;
+    }
 
     // ---- aggregation chain -------------------------------------------------------------------------------------------
     auto alloc_vectors = [&](MgLevel& L) -> int {

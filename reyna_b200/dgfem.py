@@ -67,8 +67,10 @@ class DGFEM:
 
         # Krylov replacement of spsolve (main.py:231)
         # 'preconditioner': 'auto' = multigrid ('mg') when diffusion is present, block Jacobi ('bj') otherwise
+        # 'mg_hierarchy': 'agglomerated' (P1 spaces on groups of 4 elements; defaults mg_nu 2, mg_omega 0.8, mg_alpha 2.2) or
+        # 'aggregation' (piecewise constants; defaults 3, 0.7, 1.8) -- set 'mg_nu' / 'mg_omega' / 'mg_alpha' to override
         self.solver_options = {'method': 'auto', 'rtol': 1e-14, 'max_iter': 200000, 'check_every': 10,
-                               'preconditioner': 'auto', 'mg_nu': 3, 'mg_omega': 0.7, 'mg_alpha': 1.8}
+                               'preconditioner': 'auto', 'mg_hierarchy': 'agglomerated'}
         self.solve_info: typing.Optional[dict] = None
         self.timings: dict = {}
         self.device = None         # torch device; default: current CUDA device
@@ -408,6 +410,7 @@ class DGFEM:
             blocked = False
         tm['nnz'] = int(nnz)
         return dict(indptr=indptr, indices=indices, data=data, load=load, blocked=blocked, n=N, d=d, structural=structural,
+                    bbox=gd['bbox'],
                     n_cols=int(getattr(self.geometry, 'n_global_elements', R)) * d,
                     structure=dict(adj_off=adj_off, adj_item=adj_item, adj_nb=adj_nb, grp_off=grp_off, n_items=st.n_items,
                                    n_groups=st.n_groups, n_dup_items=st.n_dup_items),
@@ -453,8 +456,13 @@ class DGFEM:
             sp = C.c_void_p(side.cuda_stream)
             try:
                 if prec == 'mg':
-                    mo = _lib.RbMgOpts(nu=int(so.get('mg_nu', 3)), omega=float(so.get('mg_omega', 0.7)),
-                                       alpha=float(so.get('mg_alpha', 1.8)))
+                    # 'agglomerated': P1 spaces on groups of 4 elements below the P1 level; 'aggregation': the
+                    # piecewise-constant chain (the only one the distributed hierarchy has)
+                    agglo = so.get('mg_hierarchy', 'agglomerated') == 'agglomerated'
+                    mo = _lib.RbMgOpts(nu=int(so.get('mg_nu', 2 if agglo else 3)),
+                                       omega=float(so.get('mg_omega', 0.8 if agglo else 0.7)),
+                                       alpha=float(so.get('mg_alpha', 2.2 if agglo else 1.8)),
+                                       elem_bbox=_ptr(dv['bbox']) if agglo else None)
                     _lib.check(L.reyna_b200_mg_create(N, d, self.polydegree, _ptr(s_indptr), _ptr(s_indices), _ptr(s_data),
                                                       C.byref(mo), None, C.byref(mg), sp), 'reyna_b200_mg_create')
                     nl = C.c_int32(0)

@@ -59,6 +59,61 @@ def test_multigrid_operator_matches_scipy_restatement(rb, E, name, p):
         L.reyna_b200_mg_destroy(mg)
 
 
+@pytest.mark.parametrize("E,name,p", [(6000, "diffusion", 2), (6000, "adr", 1), (5000, "variable", 3), (60, "diffusion", 1)])
+def test_agglomerated_multigrid_matches_scipy_restatement(rb, E, name, p):
+    """The agglomerated-P1 chain (rb_mg_opts.elem_bbox): level sizes, operator sizes and the cycle against scipy."""
+    import torch
+    from oracle.mg_reference import AgglomeratedP1
+    from reyna_b200 import _lib
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(E, seed=11), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=p)
+    dg.add_data(**PROBLEMS[name]["data"])
+    dg.dgfem(solve=False)
+    dv = dg._dev
+    assert dv["blocked"]
+    bbox = dv["bbox"].cpu().numpy()
+    ref = AgglomeratedP1(dg.B, p, bbox, nu=2, omega=0.8, alpha=2.2)
+    L = rb.lib()
+    ip, ix, dat = dv["structural"]
+    mg = C.c_void_p(None)
+    sp_ = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    mo = _lib.RbMgOpts(nu=2, omega=0.8, alpha=2.2, elem_bbox=dv["bbox"].data_ptr())
+    _lib.check(L.reyna_b200_mg_create(dv["n"], dv["d"], p, ip.data_ptr(), ix.data_ptr(), dat.data_ptr(), C.byref(mo),
+                                      None, C.byref(mg), sp_), "mg_create")
+    try:
+        nl = C.c_int32(0)
+        rows = (C.c_int32 * 16)()
+        nnz = (C.c_longlong * 16)()
+        L.reyna_b200_mg_info(mg, C.byref(nl), rows, nnz)
+        assert [rows[i] for i in range(nl.value)] == ref.level_sizes()
+        # the CUDA levels store complete 3 x 3 blocks (structural zeros included); scipy prunes nothing either
+        assert [nnz[i] for i in range(1, nl.value)] == [lv["A"].nnz for lv in ref.levels[1:]]
+        rng = np.random.default_rng(0)
+        for _ in range(2):
+            r = rng.standard_normal(dv["n"])
+            rt = torch.from_numpy(r).cuda()
+            zt = torch.empty_like(rt)
+            _lib.check(L.reyna_b200_mg_apply(mg, rt.data_ptr(), zt.data_ptr(), sp_), "mg_apply")
+            z = zt.cpu().numpy()
+            zr = ref.apply(r)
+            assert util.rel_l2(z, zr) <= 1e-10
+    finally:
+        L.reyna_b200_mg_destroy(mg)
+
+
+def test_agglomerated_hierarchy_needs_fewer_iterations(rb):
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(16384, tiles=4, seed=3), subtriangulation="fan")
+    its = {}
+    for hierarchy in ("aggregation", "agglomerated"):
+        dg = rb.DGFEM(geo, polynomial_degree=2)
+        dg.add_data(**PROBLEMS["diffusion"]["data"])
+        dg.solver_options.update(rtol=1e-8, mg_hierarchy=hierarchy)
+        dg.dgfem(solve=True)
+        assert dg.solve_info["converged"], dg.solve_info
+        its[hierarchy] = dg.solve_info["iterations"]
+    assert its["agglomerated"] <= 0.7 * its["aggregation"], its
+
+
 @pytest.mark.parametrize("name,p,limit", [("diffusion", 2, 450), ("adr", 2, 300), ("diffusion", 1, 450), ("adr_tensor", 3, 450)])
 def test_multigrid_iterations_are_mesh_independent(rb, name, p, limit):
     its = []

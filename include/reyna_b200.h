@@ -204,6 +204,17 @@ typedef struct {
     const int32_t *p0_indices; /* DEVICE [p0_nnz]            (global element ids, ascending per row)          */
     const double  *p0_data;    /* DEVICE [p0_nnz]                                                             */
     long long p0_nnz;
+    /* Agglomerated-P1 hierarchy (optional; l1_indptr == NULL selects the piecewise-constant chain above).  Element ranges must
+     * start at multiples of 4 so that no aggregate straddles two ranks.  The first agglomerated level (3 x 3 blocks, scalar
+     * CSR, GLOBAL aggregate numbering, gathered by the caller) is replicated like the P0 matrix; rb_mg_opts.elem_bbox is
+     * ignored in distributed mode. */
+    const int32_t *l1_indptr;  /* DEVICE [3*n_agg+1], n_agg = ceil(n_global_elem / 4)                         */
+    const int32_t *l1_indices; /* DEVICE [l1_nnz]                                                             */
+    const double  *l1_data;    /* DEVICE [l1_nnz]                                                             */
+    long long      l1_nnz;
+    const double  *l1_bbox;    /* DEVICE [n_agg][4]  bounding boxes of the aggregates                         */
+    const double  *l0_tr;      /* DEVICE [n_owned_elem][8]  {s00, syy, sy0, sxx, sx0, 0, 0, 0}: P1 basis of the
+                                * aggregate expressed in the element's basis (see csrc/multigrid.cu)          */
 } rb_mg_dist;
 int reyna_b200_mg_create(int32_t n_rows_scalar, int32_t d, int32_t p, const int32_t *indptr, const int32_t *indices,
                          const double *data, const rb_mg_opts *opts, const rb_mg_dist *dd, rb_mg **out, void *stream);

@@ -61,7 +61,9 @@ class RbMgOpts(C.Structure):
 class RbMgDist(C.Structure):
     _fields_ = [("dist", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("n_ghost_elem", C.c_int32),
                 ("n_global_elem", C.c_int32), ("bounds", C.c_void_p), ("p0_indptr", C.c_void_p), ("p0_indices", C.c_void_p),
-                ("p0_data", C.c_void_p), ("p0_nnz", C.c_longlong)]
+                ("p0_data", C.c_void_p), ("p0_nnz", C.c_longlong),
+                ("l1_indptr", C.c_void_p), ("l1_indices", C.c_void_p), ("l1_data", C.c_void_p), ("l1_nnz", C.c_longlong),
+                ("l1_bbox", C.c_void_p), ("l0_tr", C.c_void_p)]
 
 
 class RbSolveOpts(C.Structure):

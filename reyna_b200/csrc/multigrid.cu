@@ -67,7 +67,7 @@ struct rb_mg {
     // distributed mode: fine and P1 levels are partitioned (halo exchange), the P0 chain is global and replicated
     rb_dist* dist = nullptr;
     int n_ghost_elem = 0, lo_elem = 0;
-    std::vector<int32_t> bounds;
+    std::vector<int32_t> bounds, bounds_l1;
     std::vector<void*> owned;
     // agglomerated-P1 chain (rb_mg_opts.elem_bbox given): blev[0] is the P1 level itself
     int agg_p1 = 0, nblev = 0;
@@ -560,6 +560,10 @@ void block_jacobi_setup_launch(int n_blocks, int d, const int32_t* indptr, const
 
 static inline int mg_grid(int64_t n) { return grid_for(n, kMgThreads, kNumSMs * 8); }
 
+int dist_halo_d(rb_dist* h, double* x, int d, cudaStream_t st);                                           // dist.cu
+int dist_allgather_rows(rb_dist* h, const double* local, double* global, const int32_t* bounds, cudaStream_t st);
+
+
 // V-cycle on the P0 aggregation chain, level k: lev[k].b holds the right-hand side, the result is left in lev[k].x
 static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     MgLevel& L = mg->lev[k];
@@ -605,11 +609,15 @@ static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     }
     const int g = mg_grid(L.n);
     const bool top_blocked = (k == 0 && mg->has_p1);             // the P1 level shares the fine level's block columns
+    const bool dist0 = (k == 0 && mg->dist != nullptr);          // partitioned level: ghost coefficients behind the owned ones
+    const int ncols = dist0 ? L.n + 3 * mg->n_ghost_elem : L.n;
+    int hrc = 0;
     auto residual = [&]() {
+        if (dist0 && !hrc) hrc = dist_halo_d(mg->dist, L.x, 3, st);
         if (top_blocked)
-            mg_residual_blocked3<8><<<mg_grid((int64_t)L.n * 8), kMgThreads, 0, st>>>(L.n, L.n, L.indptr, mg->bcol, L.data, L.b, L.x, L.xt);
+            mg_residual_blocked3<8><<<mg_grid((int64_t)L.n * 8), kMgThreads, 0, st>>>(L.n, ncols, L.indptr, mg->bcol, L.data, L.b, L.x, L.xt);
         else
-            mg_residual<8><<<mg_grid((int64_t)L.n * 8), kMgThreads, 0, st>>>(L.n, L.n, L.indptr, L.indices, L.data, L.b, L.x, L.xt);
+            mg_residual<8><<<mg_grid((int64_t)L.n * 8), kMgThreads, 0, st>>>(L.n, ncols, L.indptr, L.indices, L.data, L.b, L.x, L.xt);
     };
     mg_block_apply<false><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.b, L.x);
     for (int s = 1; s < mg->nu; ++s) {
@@ -619,21 +627,30 @@ static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     RB_LAUNCH_CHECK("mgb pre-smoothing");
     MgLevel& C = mg->blev[k + 1];
     residual();
-    mgb_restrict<<<mg_grid(C.n_blk), kMgThreads, 0, st>>>(C.n_blk, L.n_blk, L.tr, L.xt, C.b);
-    RB_LAUNCH_CHECK("mgb_restrict");
-    int rc = mgb_vcycle(mg, k + 1, st);
+    int rc;
+    if (dist0) {
+        // this rank's aggregates -> slice of the global level-1 right-hand side, all-gathered; the chain below is replicated
+        const int nagg_loc = (L.n_blk + 3) / 4;
+        mgb_restrict<<<mg_grid(nagg_loc), kMgThreads, 0, st>>>(nagg_loc, L.n_blk, L.tr, L.xt, mg->p1_t0);
+        RB_LAUNCH_CHECK("mgb_restrict");
+        if (hrc) return hrc;
+        if ((rc = dist_allgather_rows(mg->dist, mg->p1_t0, C.b, mg->bounds_l1.data(), st))) return rc;
+    } else {
+        mgb_restrict<<<mg_grid(C.n_blk), kMgThreads, 0, st>>>(C.n_blk, L.n_blk, L.tr, L.xt, C.b);
+        RB_LAUNCH_CHECK("mgb_restrict");
+    }
+    rc = mgb_vcycle(mg, k + 1, st);
     if (rc) return rc;
-    mgb_prolong_add<<<mg_grid(L.n_blk), kMgThreads, 0, st>>>(L.n_blk, mg->alpha, L.tr, C.x, L.x);
+    mgb_prolong_add<<<mg_grid(L.n_blk), kMgThreads, 0, st>>>(L.n_blk, mg->alpha, L.tr, C.x + (dist0 ? 3 * (size_t)(mg->lo_elem / 4) : 0),
+                                                         L.x);
     for (int s = 0; s < mg->nu; ++s) {
         residual();
         mg_block_apply<true><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.xt, L.x);
     }
     RB_LAUNCH_CHECK("mgb post-smoothing");
-    return 0;
+    return hrc;
 }
 
-int dist_halo_d(rb_dist* h, double* x, int d, cudaStream_t st);                                           // dist.cu
-int dist_allgather_rows(rb_dist* h, const double* local, double* global, const int32_t* bounds, cudaStream_t st);
 
 // out[i] = in[offset + i]
 __global__ void mg_copy_slice(int n, const double* __restrict__ in, int offset, double* __restrict__ out) {
@@ -666,10 +683,18 @@ int mg_apply_add(rb_mg* mg, const double* r, double* z, cudaStream_t st) {
                 return 0;
             }
             MgLevel& B1 = mg->blev[1];
-            mgb_restrict<<<mg_grid(B1.n_blk), kMgThreads, 0, st>>>(B1.n_blk, B0.n_blk, B0.tr, r, B1.b);
-            RB_LAUNCH_CHECK("mgb_restrict");
+            if (mg->dist) {
+                const int nagg_loc = (B0.n_blk + 3) / 4;
+                mgb_restrict<<<mg_grid(nagg_loc), kMgThreads, 0, st>>>(nagg_loc, B0.n_blk, B0.tr, r, mg->p1_t0);
+                RB_LAUNCH_CHECK("mgb_restrict");
+                if ((rc = dist_allgather_rows(mg->dist, mg->p1_t0, B1.b, mg->bounds_l1.data(), st))) return rc;
+            } else {
+                mgb_restrict<<<mg_grid(B1.n_blk), kMgThreads, 0, st>>>(B1.n_blk, B0.n_blk, B0.tr, r, B1.b);
+                RB_LAUNCH_CHECK("mgb_restrict");
+            }
             if ((rc = mgb_vcycle(mg, 1, st))) return rc;
-            mgb_prolong_add<<<mg_grid(B0.n_blk), kMgThreads, 0, st>>>(B0.n_blk, mg->alpha, B0.tr, B1.x, z);
+            mgb_prolong_add<<<mg_grid(B0.n_blk), kMgThreads, 0, st>>>(B0.n_blk, mg->alpha, B0.tr,
+                                                                  B1.x + (mg->dist ? 3 * (size_t)(mg->lo_elem / 4) : 0), z);
             RB_LAUNCH_CHECK("mgb_prolong_add");
         }
         return 0;
@@ -744,8 +769,9 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
     const int E = mg->n_elem;
     int rc = 0;
     auto fail = [&](int code) { reyna_b200_mg_destroy(mg); return code; };
+    const bool dist_agg = dd && dd->l1_indptr && dd->l1_indices && dd->l1_data && dd->l1_bbox && dd->l0_tr;
     if (dd) {
-        if (!dd->dist || !dd->bounds || !dd->p0_indptr || !dd->p0_indices || !dd->p0_data) {
+        if (!dd->dist || !dd->bounds || (!dist_agg && (!dd->p0_indptr || !dd->p0_indices || !dd->p0_data))) {
             set_error("reyna_b200_mg_create: incomplete rb_mg_dist");
             return fail(RB_E_ARG);
         }
@@ -807,7 +833,16 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
     if (cudaGetLastError() != cudaSuccess) { set_error("reyna_b200_mg_create: mode extraction failed"); return fail(RB_E_ARG); }
 
     // ---- agglomerated-P1 chain (single-GPU hierarchy with element bounding boxes) ----------------------------------------
-    if (!dd && opts && opts->elem_bbox && d >= 3) {
+    if (dist_agg) {
+        for (int r = 0; r <= dd->world; ++r) {
+            if (r < dd->world && dd->bounds[r] % 4 != 0) {
+                set_error("reyna_b200_mg_create: element ranges of the agglomerated hierarchy must start at multiples of 4");
+                return fail(RB_E_ARG);
+            }
+            mg->bounds_l1.push_back(3 * ((dd->bounds[r] + 3) / 4));
+        }
+    }
+    if (d >= 3 && (dist_agg || (!dd && opts && opts->elem_bbox))) {
         mg->agg_p1 = 1;
         MgLevel& B0 = mg->blev[0];
         B0.n_blk = E; B0.n = 3 * E;
@@ -820,13 +855,31 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
             if ((rc = dev_alloc(mg, (void**)&B0.x, sizeof(double) * (size_t)B0.n))) return fail(rc);
         }
         B0.nnz = nblocks * 9;
-        B0.bbox = const_cast<double*>(opts->elem_bbox);
+        B0.bbox = dist_agg ? nullptr : const_cast<double*>(opts->elem_bbox);
         int32_t* scratch = nullptr;
-        if ((rc = dev_alloc(mg, (void**)&scratch, sizeof(int32_t) * (scan_scratch_ints((int64_t)E + 2) + 4)))) return fail(rc);
+        const int64_t n_scan = dist_agg ? (int64_t)dd->n_global_elem + 2 : (int64_t)E + 2;
+        if ((rc = dev_alloc(mg, (void**)&scratch, sizeof(int32_t) * (scan_scratch_ints(n_scan) + 4)))) return fail(rc);
         int* sing = nullptr;
         if ((rc = dev_alloc(mg, (void**)&sing, sizeof(int)))) return fail(rc);
         cudaMemsetAsync(sing, 0, sizeof(int), st);
         int k = 0;
+        if (dist_agg) {
+            // level 1 is the caller's replicated GLOBAL matrix; the transfer of the owned elements comes with it
+            MgLevel& C = mg->blev[1];
+            C.n_blk = (dd->n_global_elem + 3) / 4; C.n = 3 * C.n_blk;
+            C.nnz = dd->l1_nnz;
+            C.indptr = const_cast<int32_t*>(dd->l1_indptr); C.indices = const_cast<int32_t*>(dd->l1_indices);
+            C.data = const_cast<double*>(dd->l1_data); C.bbox = const_cast<double*>(dd->l1_bbox);
+            B0.tr = const_cast<double*>(dd->l0_tr);
+            if ((rc = dev_alloc(mg, (void**)&C.minv, sizeof(double) * 9 * (size_t)C.n_blk))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&C.b, sizeof(double) * (size_t)C.n))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&C.x, sizeof(double) * (size_t)C.n))) return fail(rc);
+            if ((rc = dev_alloc(mg, (void**)&C.xt, sizeof(double) * (size_t)C.n))) return fail(rc);
+            block_jacobi_setup_launch(C.n_blk, 3, C.indptr, C.indices, C.data, C.minv, sing, st);
+            mgb_scale<<<mg_grid((int64_t)9 * C.n_blk), kMgThreads, 0, st>>>((int64_t)9 * C.n_blk, mg->omega, C.minv);
+            if ((rc = dev_alloc(mg, (void**)&mg->p1_t0, sizeof(double) * 3 * ((size_t)(E + 3) / 4 + 1)))) return fail(rc);
+            k = 1;
+        }
         while (mg->blev[k].n > kDenseMax && k < kMaxLevels - 1) {
             MgLevel& L = mg->blev[k];
             MgLevel& C = mg->blev[k + 1];

@@ -173,15 +173,24 @@ class DistributedDGFEM:
             keep = []
             try:
                 if prec == "mg":
-                    mo = _lib.RbMgOpts(nu=int(so.get("mg_nu", 3)), omega=float(so.get("mg_omega", 0.7)),
-                                       alpha=float(so.get("mg_alpha", 1.8)))
-                    p0_indptr, p0_indices, p0_data = self._global_p0(torch, dev, dv)
+                    agglo = so.get("mg_hierarchy", "agglomerated") == "agglomerated"
+                    mo = _lib.RbMgOpts(nu=int(so.get("mg_nu", 2 if agglo else 3)),
+                                       omega=float(so.get("mg_omega", 0.8 if agglo else 0.7)),
+                                       alpha=float(so.get("mg_alpha", 2.2 if agglo else 1.8)))
                     bounds32 = (C.c_int32 * (self.world + 1))(*[int(b) for b in self.bounds])
-                    keep += [p0_indptr, p0_indices, p0_data, bounds32]
                     dd = _lib.RbMgDist(dist=ctx["handle"], rank=self.rank, world=self.world,
                                        n_ghost_elem=fg.n_elem - fg.n_rows, n_global_elem=int(self.bounds[-1]),
-                                       bounds=C.cast(bounds32, C.c_void_p), p0_indptr=_ptr(p0_indptr),
-                                       p0_indices=_ptr(p0_indices), p0_data=_ptr(p0_data), p0_nnz=int(p0_data.numel()))
+                                       bounds=C.cast(bounds32, C.c_void_p))
+                    if agglo:
+                        l1_indptr, l1_indices, l1_data, l1_bbox, l0_tr = self._global_level1(torch, dev, dv)
+                        keep += [l1_indptr, l1_indices, l1_data, l1_bbox, l0_tr, bounds32]
+                        dd.l1_indptr, dd.l1_indices, dd.l1_data = _ptr(l1_indptr), _ptr(l1_indices), _ptr(l1_data)
+                        dd.l1_nnz, dd.l1_bbox, dd.l0_tr = int(l1_data.numel()), _ptr(l1_bbox), _ptr(l0_tr)
+                    else:
+                        p0_indptr, p0_indices, p0_data = self._global_p0(torch, dev, dv)
+                        keep += [p0_indptr, p0_indices, p0_data, bounds32]
+                        dd.p0_indptr, dd.p0_indices, dd.p0_data = _ptr(p0_indptr), _ptr(p0_indices), _ptr(p0_data)
+                        dd.p0_nnz = int(p0_data.numel())
                     _lib.check(L.reyna_b200_mg_create(N, d, dg.polydegree, _ptr(indptr_local), _ptr(indices_local),
                                                       _ptr(s_data), C.byref(mo), C.byref(dd), C.byref(mg), sp),
                                "reyna_b200_mg_create")
@@ -244,6 +253,103 @@ class DistributedDGFEM:
         g_indptr = torch.zeros(g_nb.numel() + 1, dtype=torch.int32, device=dev)
         g_indptr[1:] = torch.cumsum(g_nb.to(torch.int64), 0).to(torch.int32)
         return g_indptr, g_cols.contiguous(), g_vals.contiguous()
+
+    def _all_gather_cat(self, torch, dev, t, dtype):
+        """Concatenation over ranks of 1-D tensors of different lengths (sizes first, then padded payloads)."""
+        import torch.distributed as dist
+        cnt = torch.tensor([t.numel()], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(cnts, cnt)
+        sizes = [int(c[0]) for c in cnts]
+        width = max(max(sizes), 1)
+        pad = torch.zeros(width, dtype=dtype, device=dev)
+        pad[:t.numel()] = t
+        outs = [torch.empty(width, dtype=dtype, device=dev) for _ in range(self.world)]
+        dist.all_gather(outs, pad)
+        return torch.cat([o[:n] for o, n in zip(outs, sizes)])
+
+    @staticmethod
+    def _box_coefficients(torch, bb):
+        hx, hy = 0.5 * (bb[:, 1] - bb[:, 0]), 0.5 * (bb[:, 3] - bb[:, 2])
+        mx, my = 0.5 * (bb[:, 1] + bb[:, 0]), 0.5 * (bb[:, 3] + bb[:, 2])
+        r = torch.rsqrt(hx * hy)
+        c01 = 0.8660254037844386 * r                      # c0 c1 of the orthonormal Legendre basis
+        return mx, my, 0.5 * r, c01 / hx, c01 / hy
+
+    def _global_level1(self, torch, dev, dv):
+        """First agglomerated level of the multigrid hierarchy (csrc/multigrid.cu), GLOBAL and replicated: every rank forms the
+        Galerkin rows of its own aggregates, ``sum_{e in G, f in H} Pe^T A1[e,f] Pf`` with the 3 x 3 mode blocks A1 of its
+        structural CSR (global column numbering) and the bounding-box transfer matrices P, and the rows are all-gathered
+        once per solve.  Returns (indptr, indices, data) of the scalar CSR matrix with complete 3 x 3 blocks, the aggregate
+        bounding boxes and the transfer coefficients of the owned elements."""
+        d, N = dv["d"], dv["n"]
+        p = self.dg.polydegree
+        s_indptr, s_indices, s_data = dv["structural"]
+        E_loc = N // d
+        lo = int(self.bounds[self.rank])
+        E_glob = int(self.bounds[-1])
+        n_agg = (E_glob + 3) // 4
+        # bounding boxes: all elements (the global geometry is replicated on the host) and all aggregates
+        bb = torch.from_numpy(np.ascontiguousarray(flat_geometry(self.global_geometry).bbox, dtype=np.float64)).to(dev).reshape(-1, 4)
+        pad = n_agg * 4 - E_glob
+        bbp = torch.cat([bb, bb[-1:].expand(pad, 4)]) if pad else bb
+        g4 = bbp.reshape(n_agg, 4, 4)
+        bb_agg = torch.stack([g4[:, :, 0].min(1).values, g4[:, :, 1].max(1).values, g4[:, :, 2].min(1).values,
+                              g4[:, :, 3].max(1).values], dim=1).contiguous()
+        agg_of = torch.arange(E_glob, device=dev) // 4
+        mxf, myf, k00f, kxf, kyf = self._box_coefficients(torch, bb)
+        mxc, myc, k00c, kxc, kyc = [a[agg_of] for a in self._box_coefficients(torch, bb_agg)]
+        tr = torch.zeros(E_glob, 8, dtype=torch.float64, device=dev)
+        tr[:, 0] = k00c / k00f
+        tr[:, 1] = kyc / kyf
+        tr[:, 2] = kyc * (myf - myc) / k00f
+        tr[:, 3] = kxc / kxf
+        tr[:, 4] = kxc * (mxf - mxc) / k00f
+        P = torch.zeros(E_glob, 3, 3, dtype=torch.float64, device=dev)     # rows: element modes, columns: aggregate modes
+        P[:, 0, 0], P[:, 0, 1], P[:, 0, 2], P[:, 1, 1], P[:, 2, 2] = tr[:, 0], tr[:, 2], tr[:, 4], tr[:, 1], tr[:, 3]
+        # 3 x 3 mode blocks of this rank's block rows
+        sel = torch.tensor([0, 1, p + 1] if d > 3 else [0, 1, 2], device=dev)
+        starts = s_indptr[0:N:d].to(torch.int64)
+        rowlen = s_indptr[1:N + 1:d].to(torch.int64) - starts
+        nb = rowlen // d
+        brow = torch.repeat_interleave(torch.arange(E_loc, device=dev), nb)
+        first = torch.cumsum(nb, 0) - nb
+        slot = torch.arange(brow.numel(), device=dev) - first[brow]
+        base = starts[brow] + slot * d                                         # entry (row mode 0, column mode 0) of the block
+        f_glob = (s_indices[base] // d).to(torch.int64)
+        pos = base[:, None, None] + sel[:, None] * rowlen[brow][:, None, None] + sel[None, :]
+        A1 = s_data[pos]                                                       # [n_blocks, 3, 3]
+        e_glob = brow + lo
+        At = torch.bmm(torch.bmm(P[e_glob].transpose(1, 2), A1), P[f_glob])
+        key = (e_glob // 4) * n_agg + f_glob // 4
+        order = torch.argsort(key, stable=True)
+        key_s, At_s = key[order], At[order]
+        ukey, inv, counts = torch.unique_consecutive(key_s, return_inverse=True, return_counts=True)
+        # deterministic segmented sum: the j-th member of every group is added in pass j (no two writes collide)
+        gstart = torch.cumsum(counts, 0) - counts
+        rank_in = torch.arange(key_s.numel(), device=dev) - gstart[inv]
+        blocks = torch.zeros(ukey.numel(), 3, 3, dtype=torch.float64, device=dev)
+        for j in range(int(counts.max().item()) if counts.numel() else 0):
+            m = rank_in == j
+            blocks[inv[m]] += At_s[m]
+        g_key = self._all_gather_cat(torch, dev, ukey, torch.int64)
+        g_blk = self._all_gather_cat(torch, dev, blocks.reshape(-1), torch.float64).reshape(-1, 3, 3)
+        G, H = g_key // n_agg, g_key % n_agg
+        nbG = torch.bincount(G, minlength=n_agg)
+        boff = torch.cumsum(nbG, 0) - nbG
+        slotG = torch.arange(G.numel(), device=dev) - boff[G]
+        i3 = torch.arange(3, device=dev)
+        posg = (9 * boff[G])[:, None, None] + i3[:, None] * (3 * nbG[G])[:, None, None] + (3 * slotG)[:, None, None] + i3[None, :]
+        nnz = int(9 * G.numel())
+        indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+        data = torch.empty(nnz, dtype=torch.float64, device=dev)
+        indices[posg.reshape(-1)] = ((3 * H)[:, None, None] + i3[None, :].expand(3, 3)).reshape(-1).to(torch.int32)
+        data[posg.reshape(-1)] = g_blk.reshape(-1)
+        indptr = torch.empty(3 * n_agg + 1, dtype=torch.int32, device=dev)
+        rows = (9 * boff)[:, None] + i3[None, :] * (3 * nbG)[:, None]
+        indptr[:-1] = rows.reshape(-1).to(torch.int32)
+        indptr[-1] = nnz
+        return indptr, indices, data, bb_agg, tr[lo:lo + E_loc].contiguous()
 
     def gather_solution(self) -> np.ndarray:
         """The global coefficient vector (element order of the unpartitioned geometry) on every rank."""

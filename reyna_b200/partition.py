@@ -22,8 +22,11 @@ from .geometry import flat_geometry
 
 
 def partition_bounds(n_elements: int, world: int) -> np.ndarray:
-    """Contiguous, balanced element ranges: rank r owns [bounds[r], bounds[r+1])."""
-    return (np.arange(world + 1, dtype=np.int64) * n_elements) // world
+    """Contiguous, balanced element ranges: rank r owns [bounds[r], bounds[r+1]).  Ranges start at multiples of 4 so that the
+    groups of 4 consecutive elements the multigrid hierarchy agglomerates never straddle two ranks."""
+    b = ((np.arange(world + 1, dtype=np.int64) * n_elements) // world) // 4 * 4
+    b[-1] = n_elements
+    return b
 
 
 def morton_partition_order(geometry) -> np.ndarray:

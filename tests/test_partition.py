@@ -93,3 +93,70 @@ def _gloo_worker(rank, world, port, n_elements, d):
 def test_gloo_halo_exchange_world2():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, 1024, 6), nprocs=2, join=True)
+
+
+def _level1_worker(rank, world, port, n_elements, p):
+    """The replicated first agglomerated multigrid level that DistributedDGFEM gathers, on CPU tensors over gloo, against the
+    scipy restatement of the hierarchy (oracle/mg_reference.py)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+        import scipy.sparse as sp
+        from oracle import dg_oracle
+        from oracle.mg_reference import AgglomeratedP1
+        from reyna_b200.distributed import DistributedDGFEM
+        from reyna_b200.problems import PROBLEMS
+        geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(n_elements, tiles=2, seed=3), subtriangulation="fan")
+        d = (p + 1) * (p + 2) // 2
+        B, _, _ = dg_oracle.assemble(geo, p, **PROBLEMS["diffusion"]["data"])
+        bsr = sp.csr_matrix(B).tobsr(blocksize=(d, d))
+        bsr.sort_indices()
+        bounds = partition_bounds(geo.n_elements, world)
+        assert np.all(bounds[:-1] % 4 == 0)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        # this rank's block rows as the structural scalar CSR the library assembles (complete blocks, global columns)
+        indptr, indices, data = [0], [], []
+        for e in range(lo, hi):
+            k0, k1 = bsr.indptr[e], bsr.indptr[e + 1]
+            cols = bsr.indices[k0:k1]
+            for i in range(d):
+                indices.append((cols[:, None] * d + np.arange(d)[None]).ravel())
+                data.append(bsr.data[k0:k1, i, :].ravel())
+                indptr.append(indptr[-1] + (k1 - k0) * d)
+        dv = dict(d=d, n=(hi - lo) * d,
+                  structural=(torch.tensor(indptr, dtype=torch.int32), torch.from_numpy(np.concatenate(indices).astype(np.int32)),
+                              torch.from_numpy(np.concatenate(data))))
+        ddg = object.__new__(DistributedDGFEM)
+        ddg.rank, ddg.world, ddg.bounds, ddg.global_geometry = rank, world, bounds, geo
+        ddg.dg = types.SimpleNamespace(polydegree=p)
+        l1_indptr, l1_indices, l1_data, bb_agg, tr = ddg._global_level1(torch, torch.device("cpu"), dv)
+        ref = AgglomeratedP1(B, p, rb.flat_geometry(geo).bbox)
+        A1 = ref.levels[1]["A"]
+        got = sp.csr_matrix((l1_data.numpy(), l1_indices.numpy(), l1_indptr.numpy()), shape=A1.shape)
+        diff = abs(got - A1)
+        assert diff.max() <= 1e-12 * abs(A1).max(), diff.max()
+        assert got.nnz == A1.nnz                                # complete 3 x 3 blocks on both sides
+        P0, bb_c = AgglomeratedP1._prolongation(np.asarray(rb.flat_geometry(geo).bbox, dtype=float).reshape(-1, 4))
+        assert np.allclose(bb_agg.numpy(), bb_c, rtol=0, atol=0)
+        Pd = P0.toarray()
+        for k, e in enumerate(range(lo, hi)):
+            G = e // 4
+            blk = Pd[3 * e:3 * e + 3, 3 * G:3 * G + 3]
+            want = np.array([blk[0, 0], blk[1, 1], blk[0, 1], blk[2, 2], blk[0, 2]])
+            assert np.allclose(tr[k, :5].numpy(), want, rtol=1e-14, atol=0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_global_multigrid_level_world2():
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_level1_worker, args=(2, port, 256, 2), nprocs=2, join=True)
+
+
+def test_partition_bounds_keep_aggregates_on_one_rank():
+    for n, world in ((1000, 3), (1048576, 8), (1023, 2), (17, 4)):
+        b = partition_bounds(n, world)
+        assert b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0) and np.all(b[:-1] % 4 == 0)

@@ -598,6 +598,50 @@ static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
 }
 
 
+
+// One sweep on a 3 x 3-block level, 8 lanes per BLOCK row (its three scalar rows are contiguous and share their columns):
+// every x value is gathered once and used for the three rows.  SWEEP == false: out = b - A x;  SWEEP == true: the damped block
+// Jacobi update out = x + Minv (b - A x) (omega folded into minv), written to another buffer than x.  Columns >= ncols are
+// ghost couplings the level ignores.  Fixed shuffle tree: deterministic.
+template <bool SWEEP>
+__global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols, const int32_t* __restrict__ indptr,
+                                                            const int32_t* __restrict__ indices, const double* __restrict__ data,
+                                                            const double* __restrict__ minv, const double* __restrict__ b,
+                                                            const double* __restrict__ x, double* __restrict__ out) {
+    const int lane = threadIdx.x & 7;
+    const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / 8;
+    for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8; e < n_blk; e += stride) {
+        const int lo = indptr[3 * e];
+        const int len = indptr[3 * e + 1] - lo;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int j = lane; j < len; j += 8) {
+            const int c = indices[lo + j];
+            if (c < ncols) {
+                const double xv = x[c];
+                s0 = fma(data[lo + j], xv, s0);
+                s1 = fma(data[lo + len + j], xv, s1);
+                s2 = fma(data[lo + 2 * len + j], xv, s2);
+            }
+        }
+#pragma unroll
+        for (int o = 4; o; o >>= 1) {
+            s0 += __shfl_xor_sync(gm, s0, o, 8);
+            s1 += __shfl_xor_sync(gm, s1, o, 8);
+            s2 += __shfl_xor_sync(gm, s2, o, 8);
+        }
+        if (lane < 3) {
+            const double r0 = b[3 * e] - s0, r1 = b[3 * e + 1] - s1, r2 = b[3 * e + 2] - s2;
+            if (SWEEP) {
+                const double* m = minv + 9 * (size_t)e + 3 * lane;
+                out[3 * e + lane] = x[3 * e + lane] + fma(m[0], r0, fma(m[1], r1, m[2] * r2));
+            } else {
+                out[3 * e + lane] = lane == 0 ? r0 : (lane == 1 ? r1 : r2);
+            }
+        }
+    }
+}
+
 // V-cycle on the agglomerated-P1 chain, level k: blev[k].b holds the right-hand side, the result is left in blev[k].x.
 // Smoother: nu sweeps of 3 x 3 block Jacobi (the damping is folded into minv), coarse corrections scaled by alpha.
 static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
@@ -608,47 +652,41 @@ static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
         return 0;
     }
     const int g = mg_grid(L.n);
-    const bool top_blocked = (k == 0 && mg->has_p1);             // the P1 level shares the fine level's block columns
+    const int gb = mg_grid((int64_t)L.n_blk * 8);
     const bool dist0 = (k == 0 && mg->dist != nullptr);          // partitioned level: ghost coefficients behind the owned ones
     const int ncols = dist0 ? L.n + 3 * mg->n_ghost_elem : L.n;
-    int hrc = 0;
-    auto residual = [&]() {
-        if (dist0 && !hrc) hrc = dist_halo_d(mg->dist, L.x, 3, st);
-        if (top_blocked)
-            mg_residual_blocked3<8><<<mg_grid((int64_t)L.n * 8), kMgThreads, 0, st>>>(L.n, ncols, L.indptr, mg->bcol, L.data, L.b, L.x, L.xt);
-        else
-            mg_residual<8><<<mg_grid((int64_t)L.n * 8), kMgThreads, 0, st>>>(L.n, ncols, L.indptr, L.indices, L.data, L.b, L.x, L.xt);
+    int rc = 0;
+    // the iterate ping-pongs between L.xt and L.x; 2 nu - 1 sweeps in total, so starting in L.xt it ends in L.x
+    double *cur = L.xt, *oth = L.x;
+    mg_block_apply<false><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.b, cur);
+    auto sweep = [&]() {
+        if (dist0 && !rc) rc = dist_halo_d(mg->dist, cur, 3, st);
+        mgb_block_row<true><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth);
+        double* t = cur; cur = oth; oth = t;
     };
-    mg_block_apply<false><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.b, L.x);
-    for (int s = 1; s < mg->nu; ++s) {
-        residual();
-        mg_block_apply<true><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.xt, L.x);
-    }
+    for (int s = 1; s < mg->nu; ++s) sweep();
     RB_LAUNCH_CHECK("mgb pre-smoothing");
     MgLevel& C = mg->blev[k + 1];
-    residual();
-    int rc;
+    if (dist0 && !rc) rc = dist_halo_d(mg->dist, cur, 3, st);
+    if (rc) return rc;
+    mgb_block_row<false><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth);
     if (dist0) {
         // this rank's aggregates -> slice of the global level-1 right-hand side, all-gathered; the chain below is replicated
         const int nagg_loc = (L.n_blk + 3) / 4;
-        mgb_restrict<<<mg_grid(nagg_loc), kMgThreads, 0, st>>>(nagg_loc, L.n_blk, L.tr, L.xt, mg->p1_t0);
+        mgb_restrict<<<mg_grid(nagg_loc), kMgThreads, 0, st>>>(nagg_loc, L.n_blk, L.tr, oth, mg->p1_t0);
         RB_LAUNCH_CHECK("mgb_restrict");
-        if (hrc) return hrc;
         if ((rc = dist_allgather_rows(mg->dist, mg->p1_t0, C.b, mg->bounds_l1.data(), st))) return rc;
     } else {
-        mgb_restrict<<<mg_grid(C.n_blk), kMgThreads, 0, st>>>(C.n_blk, L.n_blk, L.tr, L.xt, C.b);
+        mgb_restrict<<<mg_grid(C.n_blk), kMgThreads, 0, st>>>(C.n_blk, L.n_blk, L.tr, oth, C.b);
         RB_LAUNCH_CHECK("mgb_restrict");
     }
-    rc = mgb_vcycle(mg, k + 1, st);
-    if (rc) return rc;
+    if ((rc = mgb_vcycle(mg, k + 1, st))) return rc;
     mgb_prolong_add<<<mg_grid(L.n_blk), kMgThreads, 0, st>>>(L.n_blk, mg->alpha, L.tr, C.x + (dist0 ? 3 * (size_t)(mg->lo_elem / 4) : 0),
-                                                         L.x);
-    for (int s = 0; s < mg->nu; ++s) {
-        residual();
-        mg_block_apply<true><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.xt, L.x);
-    }
+                                                         cur);
+    for (int s = 0; s < mg->nu; ++s) sweep();
     RB_LAUNCH_CHECK("mgb post-smoothing");
-    return hrc;
+    if (cur != L.x) RB_CUDA(cudaMemcpyAsync(L.x, cur, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, st));   // nu == 0 only
+    return rc;
 }
 
 
@@ -814,7 +852,8 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
         if ((rc = dev_alloc(mg, (void**)&mg->p1_r, sizeof(double) * (size_t)n1))) return fail(rc);
         if ((rc = dev_alloc(mg, (void**)&mg->p1_x, sizeof(double) * ((size_t)n1 + 3 * (size_t)mg->n_ghost_elem)))) return fail(rc);
         RB_CUDA(cudaMemsetAsync(mg->p1_x, 0, sizeof(double) * ((size_t)n1 + 3 * (size_t)mg->n_ghost_elem), st));
-        if ((rc = dev_alloc(mg, (void**)&mg->p1_t, sizeof(double) * (size_t)n1))) return fail(rc);
+        if ((rc = dev_alloc(mg, (void**)&mg->p1_t, sizeof(double) * ((size_t)n1 + 3 * (size_t)mg->n_ghost_elem)))) return fail(rc);
+        RB_CUDA(cudaMemsetAsync(mg->p1_t, 0, sizeof(double) * ((size_t)n1 + 3 * (size_t)mg->n_ghost_elem), st));
         mg_extract_modes<<<mg_grid(n1), kMgThreads, 0, st>>>(E, d, 3, mg->sel1[0], mg->sel1[1], mg->sel1[2], indptr, indices,
                                                             data, mg->p1_indptr, mg->p1_indices, mg->p1_data);
         if ((rc = dev_alloc(mg, (void**)&mg->bcol, sizeof(int32_t) * (size_t)(nblocks + 1)))) return fail(rc);

@@ -104,6 +104,20 @@ __device__ __forceinline__ ElemBox read_box(double2* s, int tid, int base_plane)
     return b;
 }
 
+
+// One 6-double row of a block at a 16-byte aligned address: a 32-byte and a 16-byte store (STG.256 + STG.128), the 32-byte one
+// on whichever half is sector aligned -- two global store operations per row instead of three (the kernel is bound by the
+// number of per-lane global operations, profiles/r01_assemble_experiments.md).
+__device__ __forceinline__ void store_row6(double* dst, double v0, double v1, double v2, double v3, double v4, double v5) {
+    const bool al = (reinterpret_cast<size_t>(dst) & 31) == 0;
+    double* p4 = al ? dst : dst + 2;
+    double* p2 = al ? dst + 4 : dst;
+    const double a0 = al ? v0 : v2, a1 = al ? v1 : v3, a2 = al ? v2 : v4, a3 = al ? v3 : v5;
+    const double b0 = al ? v4 : v0, b1 = al ? v5 : v1;
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p4), "d"(a0), "d"(a1), "d"(a2), "d"(a3) : "memory");
+    *reinterpret_cast<double2*>(p2) = make_double2(b0, b1);
+}
+
 struct FaceGeo {
     double midx, midy, tanx, tany, nx, ny, De, sigma;
 };
@@ -278,7 +292,11 @@ __device__ __forceinline__ void face_pass(const AsmArgs& A, int e, int eg, const
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
                     double* dst = A.data + row_base + (int64_t)j * rowlen + (int64_t)slot * D + I0;
-                    if (RS == 1 && (D & 1) == 0) {
+                    if (RS == 1 && D == 6) {
+                        store_row6(dst, oacc[j * 6], oacc[j * 6 + 1], oacc[j * 6 + 2], oacc[j * 6 + 3], oacc[j * 6 + 4], oacc[j * 6 + 5]);
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) zeros += (oacc[j * 6 + i] == 0.0);
+                    } else if (RS == 1 && (D & 1) == 0) {
 #pragma unroll
                         for (int i = 0; i < D; i += 2) {
                             reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(oacc[j * CI + i], oacc[j * CI + i + 1]);
@@ -429,8 +447,12 @@ __device__ __forceinline__ void element_work(const AsmArgs& A, int e, double2* s
         __pipeline_wait_prior(0);
     }
     // load vector rows of this part
+    if (RS == 1 && D == 6) {
+        store_row6(A.load + (size_t)e * 6, acc[NA], acc[NA + 1], acc[NA + 2], acc[NA + 3], acc[NA + 4], acc[NA + 5]);
+    } else {
 #pragma unroll
-    for (int ii = 0; ii < CI; ++ii) A.load[(size_t)e * D + I0 + ii] = acc[NA + ii];
+        for (int ii = 0; ii < CI; ++ii) A.load[(size_t)e * D + I0 + ii] = acc[NA + ii];
+    }
 
     // ---- phases D / O: interior faces ---------------------------------------------------------------------------------
     const int nb = (g1 - g0) + 1;
@@ -446,7 +468,11 @@ __device__ __forceinline__ void element_work(const AsmArgs& A, int e, double2* s
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         double* dst = A.data + row_base + (int64_t)j * rowlen + (int64_t)dslot * D + I0;
-        if (RS == 1 && (D & 1) == 0) {
+        if (RS == 1 && D == 6) {
+            store_row6(dst, acc[j * 6], acc[j * 6 + 1], acc[j * 6 + 2], acc[j * 6 + 3], acc[j * 6 + 4], acc[j * 6 + 5]);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) zeros += (acc[j * 6 + i] == 0.0);
+        } else if (RS == 1 && (D & 1) == 0) {
 #pragma unroll
             for (int i = 0; i < D; i += 2) {
                 reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(acc[j * CI + i], acc[j * CI + i + 1]);

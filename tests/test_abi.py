@@ -41,7 +41,7 @@ def test_ctypes_structs_match_header_sizes():
     from reyna_b200 import _lib
     names = [("rb_geom", _lib.RbGeom), ("rb_quad", _lib.RbQuad), ("rb_coefs", _lib.RbCoefs),
              ("rb_structure", _lib.RbStructure), ("rb_solve_opts", _lib.RbSolveOpts), ("rb_solve_info", _lib.RbSolveInfo),
-             ("rb_err_samples", _lib.RbErrSamples)]
+             ("rb_err_samples", _lib.RbErrSamples), ("rb_mg_opts", _lib.RbMgOpts), ("rb_mg_dist", _lib.RbMgDist)]
     names = [(n, t) for n, t in names if re.search(r"\b%s\b" % n, open(HEADER).read())]
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "s.c")
@@ -55,6 +55,29 @@ def test_ctypes_structs_match_header_sizes():
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     for (n, t), size in zip(names, out):
         assert ctypes.sizeof(t) == int(size), n
+
+
+def test_ctypes_field_offsets_match_header():
+    """offsetof() of every field of the option / distribution structs (a reordered field keeps the size)."""
+    import subprocess
+    import tempfile
+    from reyna_b200 import _lib
+    structs = [("rb_mg_opts", _lib.RbMgOpts), ("rb_mg_dist", _lib.RbMgDist), ("rb_solve_opts", _lib.RbSolveOpts),
+               ("rb_solve_info", _lib.RbSolveInfo), ("rb_structure", _lib.RbStructure), ("rb_coefs", _lib.RbCoefs)]
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "o.c")
+        with open(src, "w") as fh:
+            fh.write('#include <stdio.h>\n#include <stddef.h>\n#include "reyna_b200.h"\nint main(void){\n')
+            for n, t in structs:
+                for f in t._fields_:
+                    fh.write(f'printf("%zu\\n", offsetof({n}, {f[0]}));\n')
+            fh.write("return 0;}\n")
+        exe = os.path.join(td, "o")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = iter(subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
+    for n, t in structs:
+        for f in t._fields_:
+            assert getattr(t, f[0]).offset == int(next(out)), (n, f[0])
 
 
 def test_no_cpu_fallback_without_cuda():

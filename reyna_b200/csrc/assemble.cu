@@ -766,7 +766,7 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
         RB_LAUNCH_CHECK("dg_prepare_kernel");
     }
     // threads per item: whole blocks per thread for p <= 2 (measured faster on B200 than column halves at 12 warps per
-    // SM, profiles/r01_assemble_tuning.md), column halves for p = 3; REYNA_B200_RS=2 selects halves at p = 2 (A/B aid)
+    // SM), column halves for p = 3; REYNA_B200_RS=2 selects halves at p = 2 (A/B aid)
     int rs = p >= 3 ? 2 : 1;
     if (const char* env = getenv("REYNA_B200_RS")) { if (atoi(env) == 2 && p == 2) rs = 2; }
     const double items_per_elem = (double)s->n_items / g->n_rows;

@@ -18,7 +18,8 @@
  *   DoF (e,k) -> e*d + k, d = (p+1)(p+2)/2, k enumerates (i,j), i+j<=p row-major
  *   (polygonal_basis_utils.py:7-26).  The matrix is scalar CSR whose rows (e,j) hold, per neighbouring element in
  *   ascending order (the element itself included), d consecutive columns: exactly scipy's canonical CSR of B.
- *   Coefficient samples are "q-major": value of quadrature point q of item t at [q*n_items + t].
+ *   Face and boundary coefficient samples are "q-major": value of quadrature point q of item t at [q*n_items + t];
+ *   volume samples follow the round order described at rb_geom.
  */
 #ifndef REYNA_B200_H
 #define REYNA_B200_H
@@ -63,6 +64,17 @@ typedef struct {
     const double  *bnorm;      /* [n_bface][2] outward              geometry.boundary_normals                */
     const int32_t *elem_gid;   /* [n_elem] global element id of every local element (multi-GPU partitions: block columns are
                                   ordered and numbered by it); NULL = identity                              */
+    /* Volume stream (host-built once per geometry, reyna_b200/stream.py): sub-triangles are packed, in order, into
+     * "volume rounds" of whole elements with at most 32 triangles (one warp, one lane per triangle).  An element with
+     * more than 32 triangles fills rounds of its own; its pieces are "segments".  The volume samples of rb_coefs are
+     * ordered round by round, q-major inside a round: sample q of the l-th triangle of round r (n_r triangles, first
+     * triangle t_r = vround_tri0[r]) sits at index Qv*t_r + q*n_r + l -- every round is one contiguous range.        */
+    const double  *tri_xy;     /* [n_tri][3][2] vertex coordinates of every sub-triangle (nodes[tri])         */
+    const int32_t *vround_tri0;/* [n_vrounds+1] first triangle of every volume round                          */
+    const int32_t *tri_seg;    /* [n_tri] segment of every triangle; NULL = tri_elem (no element has > 32 triangles) */
+    const int32_t *elem_seg0;  /* [n_rows+1] first segment of every element; NULL = identity                  */
+    int32_t n_vrounds;
+    int32_t n_vsegs;           /* number of segments (== n_rows when elem_seg0 is NULL)                       */
 } rb_geom;
 
 /* Reference quadrature (HOST arrays; DGFEM._intialise_quadrature, main.py:233-257). */
@@ -78,10 +90,12 @@ typedef struct {
  * in full_assembly.py:57,65,69,73,140,159,194-195 and boundary_assembly.py:44-45,103,111-112).  NULL <=> the
  * coefficient is None. */
 typedef struct {
-    const double *vol_a;       /* [Qv][n_tri][2][2]  diffusion at volume points                               */
-    const double *vol_b;       /* [Qv][n_tri][2]     advection                                                */
-    const double *vol_c;       /* [Qv][n_tri]        reaction                                                 */
-    const double *vol_f;       /* [Qv][n_tri]        forcing                                                  */
+    /* volume samples: [Qv*n_tri] items in the round order of rb_geom (NOT q-major over the whole mesh); vol_c / vol_f
+     * must be readable up to the next 16-byte boundary behind their last sample (bulk copies move 16-byte units) */
+    const double *vol_a;       /* [Qv*n_tri][2][2]   diffusion at volume points                               */
+    const double *vol_b;       /* [Qv*n_tri][2]      advection                                                */
+    const double *vol_c;       /* [Qv*n_tri]         reaction                                                 */
+    const double *vol_f;       /* [Qv*n_tri]         forcing                                                  */
     const double *if_a;        /* [Qe][n_iface][2][2]                                                         */
     const double *if_b;        /* [Qe][n_iface][2]                                                            */
     const double *if_a_mid;    /* [n_iface][2][2]    diffusion at the edge midpoint                           */
@@ -126,8 +140,10 @@ int reyna_b200_csr_pattern_local(const rb_geom *g, const rb_structure *s, int p,
  * (replaces DGFEM._stiffness_matrix + localstiff, main.py:275-327 / full_assembly.py:9-77, and
  * DGFEM._interior_stiffness_matrix + int_localstiff, main.py:329-374 / full_assembly.py:80-214).
  * data [nnz], load [n_rows*d]; *zero_count (device int64, caller-zeroed) receives the number of exact zeros written.
- * workspace: reyna_b200_assemble_workspace() bytes of device scratch (per-element basis scalings, per-face penalties). */
-size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface);
+ * workspace: reyna_b200_assemble_workspace() bytes of device scratch (per-element basis scalings, per-face records,
+ * per-segment volume sums).  Limits of the item-per-lane kernels (RB_E_ARG otherwise): at most 32 contributing
+ * interior faces per element (rb_structure.max_items) and at most 8 volume segments (256 sub-triangles) per element. */
+size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface, int32_t n_vsegs, int32_t p);
 int reyna_b200_assemble(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
                         double sigma_D, double *data, double *load, long long *zero_count, void *workspace,
                         size_t workspace_bytes, void *stream);

@@ -31,7 +31,9 @@ EXPORTS = (
 class RbGeom(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_nodes", "n_elem", "n_rows", "n_tri", "n_iface", "n_bface")] + \
                [(n, C.c_void_p) for n in ("nodes", "tri", "tri_elem", "tri_off", "bbox", "area", "poly_off", "poly_vtx",
-                                          "iedge", "ielem", "inorm", "bedge", "belem", "bnorm", "elem_gid")]
+                                          "iedge", "ielem", "inorm", "bedge", "belem", "bnorm", "elem_gid",
+                                          "tri_xy", "vround_tri0", "tri_seg", "elem_seg0")] + \
+               [(n, C.c_int32) for n in ("n_vrounds", "n_vsegs")]
 
 
 class RbQuad(C.Structure):
@@ -133,7 +135,7 @@ def lib() -> C.CDLL:
     L.reyna_b200_assemble.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.POINTER(RbCoefs), C.POINTER(RbQuad),
                                       C.c_double, vp, vp, i64p, vp, C.c_size_t, vp]
     L.reyna_b200_assemble_workspace.restype = C.c_size_t
-    L.reyna_b200_assemble_workspace.argtypes = [i32, i32]
+    L.reyna_b200_assemble_workspace.argtypes = [i32, i32, i32, i32]
     L.reyna_b200_boundary.restype = C.c_int
     L.reyna_b200_boundary.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.POINTER(RbCoefs), C.POINTER(RbQuad),
                                       C.c_double, i32, vp, vp, vp, vp, vp, vp, vp, i64p, vp]

@@ -1,5 +1,5 @@
-// Shared declarations of the DG assembly kernels (assemble.cu: CTA-cooperative kernel, assemble_elem.cu: element-streaming
-// kernel).
+// Shared declarations of the DG assembly kernels (assemble.cu: prepass + C entry point, assemble_items.cu: volume and face
+// kernels).
 #pragma once
 #include "basis.cuh"
 
@@ -28,17 +28,16 @@ struct AsmArgs {
     double* data;
     double* load;
     unsigned long long* zero_count;
-    int te;            // elements per CTA
     int has_dups;      // adjacency contains merged (duplicate-neighbour) items
     const ElemBox* ebox;   // [n_elem]  bounding-box scalings, written by dg_prepare_kernel
-    const double* fsigma;  // [n_iface] SIPG penalty per interior face (diffusion only), written by dg_prepare_kernel
-    const FaceRec* frec;   // [n_iface] flattened face geometry, written by dg_prepare_kernel
+    const FaceRec* frec;   // [n_iface] flattened face geometry + SIPG penalty, written by dg_prepare_kernel
     const int32_t* adj_nb; // [n_items] neighbour element of every adjacency item (rb_structure.adj_nb)
-    int32_t* perm;         // [n_rows] lane-balancing element order of the streaming kernel (workspace)
+    double* vdiag;         // [n_vsegs][d*d+d] per-segment volume sums (block + load): dg_volume_kernel -> dg_face_kernel
 };
 
-
-// element-streaming kernel (assemble_elem.cu)
-int launch_assemble_elem(const AsmArgs& A, int p, bool diff, bool adv, cudaStream_t st);
+// item-per-lane kernels (assemble_items.cu)
+int launch_assemble_items(const AsmArgs& A, int p, bool diff, bool adv, cudaStream_t st);
+int items_max_face_items();
+int items_max_segments();
 
 }  // namespace rb

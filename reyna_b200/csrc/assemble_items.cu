@@ -1,0 +1,786 @@
+// Item-per-lane DG assembly for B200: two kernels, both one warp per CTA, both fed and drained by the TMA / async-copy
+// engines instead of per-lane global loads and stores.
+//
+// Replaces DGFEM._stiffness_matrix + localstiff (reyna/DGFEM/two_dimensional/main.py:275-327, full_assembly.py:9-77),
+// DGFEM._interior_stiffness_matrix + int_localstiff (main.py:329-374, full_assembly.py:80-214) and the scipy COO->CSR
+// summation (main.py:319-320, 371-372, 211) for all elements at once.
+//
+//   dg_volume_kernel   one lane per SUB-TRIANGLE.  A CTA is one "volume round": <= 32 consecutive sub-triangles of whole
+//                      elements (the host packs rounds greedily, rb_geom.vround_tri0).  The coefficient samples of a round
+//                      are ONE contiguous range of every sample array (layout: [round][q][lane]) and the vertex
+//                      coordinates one contiguous range of rb_geom.tri_xy, so a single elected lane fetches everything
+//                      with five cp.async.bulk (1-D TMA) copies completing on one mbarrier -- no per-lane LDGSTS.  Every
+//                      lane contracts its triangle into a private d x d block (+ load) in registers, the blocks of an
+//                      element's triangles are summed IN TRIANGLE ORDER through shared memory (the order of main.py:315)
+//                      and the per-element sums go to a scratch array with fully coalesced 16-byte stores.
+//   dg_face_kernel     one lane per (element, interior face) item.  A CTA walks a window of consecutive elements in
+//                      rounds of whole elements with <= 32 items.  Face record, neighbour scalings and face samples are
+//                      staged ONCE per item by cp.async (double buffered, one round ahead), both blocks of the item are
+//                      formed from that one staging: the diagonal contributions are summed per element in item order
+//                      (after the volume sums), the off-diagonal block goes to its final CSR slot.  All block rows of a
+//                      round are CONTIGUOUS in the CSR value array, so they are collected in shared memory and written
+//                      by ONE cp.async.bulk.global.shared::cta store -- no per-lane scattered STG.
+// Bitwise reproducible: no floating-point atomics, every sum has a fixed order that does not depend on the partition.
+#include "assemble_common.cuh"
+#include <cuda_pipeline.h>
+
+namespace rb {
+namespace items {
+
+constexpr int kWarp = 32;
+constexpr int kMaxE = 8;        // elements per face round (bounds the shared-memory row buffer)
+constexpr int kMaxSeg = 8;      // volume segments staged per face round
+constexpr int kWindow = 64;     // consecutive elements per face CTA
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- PTX: mbarrier + bulk async copies ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded spin: a copy that never lands (a bug) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (unsigned spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (ok) return;
+        if (spin > (1u << 20)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+                 "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ int gid_of(const AsmArgs& A, int e) { return A.g.elem_gid ? A.g.elem_gid[e] : e; }
+
+template <int P, int RS>
+struct Dm {
+    static constexpr int D = (P + 1) * (P + 2) / 2;
+    static constexpr int DD = D * D;
+    static constexpr int NV = DD + D;          // values per element sum: block + load
+    static constexpr int QV = (P + 1) * (P + 1);
+    static constexpr int QE = P + 1;
+    static constexpr int RJ = D / RS;          // block rows per pass
+    static constexpr int NB = RJ * D;          // block values per pass
+    static_assert(D % RS == 0, "row split must divide the local dimension");
+    static_assert(RS == 1 || (NB % 2 == 0 && D % 2 == 0), "row parts must be pair aligned");
+    // volume pass `part`: NB block values (+ all D load values in the last part)
+    static constexpr int NVAL_LAST = NB + D;
+    static constexpr int NPAIR_MAX = (NVAL_LAST + 1) / 2;
+};
+
+constexpr int kPartStride = 33;   // double2 per pair row of the partial buffer (33: conflict-free column walks)
+
+
+// destination (in doubles, inside an element's NV-value record) of value pair kk of pass PART: block rows of the part,
+// then -- in the last part -- the load entries
+template <int P, int RS, int PART>
+__device__ __forceinline__ int pair_dst(int kk) {
+    using DM = Dm<P, RS>;
+    if (RS == 1) return 2 * kk;
+    if (2 * kk < DM::NB) return PART * DM::NB + 2 * kk;
+    return DM::DD + (2 * kk - DM::NB);
+}
+
+// =======================================================================================================================
+// volume kernel
+// =======================================================================================================================
+template <int P, int RS, bool DIFF, bool ADV>
+struct VolSmem {
+    using DM = Dm<P, RS>;
+    static constexpr int SZA = DIFF ? DM::QV * 32 * 32 : 0;
+    static constexpr int SZB = ADV ? DM::QV * 32 * 16 : 0;
+    static constexpr int SZC = DM::QV * 32 * 8 + 16;
+    static constexpr int OA = 0, OB = OA + SZA, OC = OB + SZB, OF = OC + SZC, SAMPLES = OF + SZC;
+    static constexpr int PARTB = DM::NPAIR_MAX * kPartStride * 16;
+    // one pass: the partial blocks overwrite the consumed samples; several passes: the samples have to survive
+    static constexpr int OPART = RS == 1 ? 0 : SAMPLES;
+    static constexpr int OXY = RS == 1 ? ((SAMPLES > PARTB ? SAMPLES : PARTB) + 15) / 16 * 16 : SAMPLES + PARTB;
+    static constexpr int OMETA = OXY + 32 * 48;                          // int s_start[36], s_seg[36]
+    static constexpr int OBAR = OMETA + 4 * 72;
+    static constexpr int TOTAL = OBAR + 16;
+};
+
+// One pass over the quadrature points of the lane's triangle: rows [J0, J0+RJ) of the local block (+ the load in the last part).
+template <int P, int RS, int PART, bool DIFF, bool ADV>
+__device__ __forceinline__ void volume_pass(const AsmArgs& A, const unsigned char* __restrict__ sm, int lane, int n, int hc, int hf,
+                                            const ElemBox& bx, double2 V0, double2 V1, double2 V2, double hdet, bool has_c,
+                                            bool has_f, double* __restrict__ acc) {
+    using DM = Dm<P, RS>;
+    using S = VolSmem<P, RS, DIFF, ADV>;
+    constexpr int D = DM::D, RJ = DM::RJ, NB = DM::NB, QV = DM::QV, J0 = PART * RJ;
+    constexpr bool LAST = PART == RS - 1;
+#pragma unroll 1
+    for (int q = 0; q < QV; ++q) {
+        const int idx = q * n + lane;
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
+        const double r0 = A.rvx[q], r1 = A.rvy[q];
+        const double l0 = 1.0 - r0 - r1;
+        const double x = l0 * V0.x + r0 * V1.x + r1 * V2.x;      // assembly_aux.py:7-29
+        const double y = l0 * V0.y + r0 * V1.y + r1 * V2.y;
+        const double W = hdet * A.wv[q];
+        if (DIFF) {
+            const double2 ra = *reinterpret_cast<const double2*>(sm + S::OA + (size_t)idx * 32);
+            const double2 rb = *reinterpret_cast<const double2*>(sm + S::OA + (size_t)idx * 32 + 16);
+            a00 = W * ra.x; a01 = W * ra.y; a10 = W * rb.x; a11 = W * rb.y;
+        }
+        if (ADV) {
+            const double2 bb = *reinterpret_cast<const double2*>(sm + S::OB + (size_t)idx * 16);
+            b0 = W * bb.x; b1 = W * bb.y;
+        }
+        const double cq = has_c ? W * *reinterpret_cast<const double*>(sm + S::OC + hc + (size_t)idx * 8) : 0.0;
+        const double wf = (LAST && has_f) ? W * *reinterpret_cast<const double*>(sm + S::OF + hf + (size_t)idx * 8) : 0.0;
+        double phi[D], gx[D], gy[D];
+        eval_basis<P, true>(x, y, bx, A.lc, phi, gx, gy);
+        // column (trial i) quantities u = W * grad(phi_i)^T a, s = W * (b.grad(phi_i) + c phi_i)   (full_assembly.py:57-77)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const bool nzx = gx_nz<P>(i), nzy = gy_nz<P>(i);     // compile-time after unrolling
+            double u0 = 0, u1 = 0;
+            if (DIFF) {
+                if (nzx && nzy) {
+                    u0 = fma(gx[i], a00, gy[i] * a10);
+                    u1 = fma(gx[i], a01, gy[i] * a11);
+                } else if (nzx) {
+                    u0 = gx[i] * a00;
+                    u1 = gx[i] * a01;
+                } else if (nzy) {
+                    u0 = gy[i] * a10;
+                    u1 = gy[i] * a11;
+                }
+            }
+            double si = cq * phi[i];
+            if (ADV && nzy) si = fma(b1, gy[i], si);
+            if (ADV && nzx) si = fma(b0, gx[i], si);
+#pragma unroll
+            for (int jj = 0; jj < RJ; ++jj) {
+                const int j = J0 + jj;
+                double v = acc[jj * D + i];
+                if (DIFF && (nzx || nzy)) {
+                    if (gx_nz<P>(j)) v = fma(u0, gx[j], v);
+                    if (gy_nz<P>(j)) v = fma(u1, gy[j], v);
+                }
+                v = fma(si, phi[j], v);
+                acc[jj * D + i] = v;
+            }
+        }
+        if (LAST && has_f) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) acc[NB + j] = fma(wf, phi[j], acc[NB + j]);
+        }
+    }
+}
+
+template <int P, int RS, int PART, bool DIFF, bool ADV>
+__device__ __forceinline__ void volume_part(const AsmArgs& A, unsigned char* __restrict__ sm, int lane, int n, int hc, int hf,
+                                            bool active, const ElemBox& bx, double2 V0, double2 V1, double2 V2, double hdet,
+                                            bool has_c, bool has_f, int nseg) {
+    using DM = Dm<P, RS>;
+    using S = VolSmem<P, RS, DIFF, ADV>;
+    constexpr bool LAST = PART == RS - 1;
+    constexpr int NVAL = DM::NB + (LAST ? DM::D : 0);
+    constexpr int NP = (NVAL + 1) / 2;
+    double acc[2 * NP];
+#pragma unroll
+    for (int v = 0; v < 2 * NP; ++v) acc[v] = 0.0;
+    if (active) volume_pass<P, RS, PART, DIFF, ADV>(A, sm, lane, n, hc, hf, bx, V0, V1, V2, hdet, has_c, has_f, acc);
+    __syncwarp();                                   // every lane is done with the samples / the previous part's partials
+    double2* part = reinterpret_cast<double2*>(sm + S::OPART);
+    if (active) {
+#pragma unroll
+        for (int kk = 0; kk < NP; ++kk) part[kk * kPartStride + lane] = make_double2(acc[2 * kk], acc[2 * kk + 1]);
+    }
+    __syncwarp();
+    const int* s_start = reinterpret_cast<const int*>(sm + S::OMETA);
+    const int* s_seg = s_start + 36;
+    const int total = nseg * NP;
+    for (int w = lane; w < total; w += kWarp) {
+        const int s = w / NP, kk = w - s * NP;
+        const int l0 = s_start[s], l1 = s_start[s + 1];
+        double2 v = part[kk * kPartStride + l0];
+        for (int l = l0 + 1; l < l1; ++l) {         // triangles in order (main.py:315)
+            const double2 t = part[kk * kPartStride + l];
+            v.x += t.x;
+            v.y += t.y;
+        }
+        double* dst = A.vdiag + (size_t)s_seg[s] * DM::NV + pair_dst<P, RS, PART>(kk);
+        if (2 * kk + 1 < NVAL) *reinterpret_cast<double2*>(dst) = v;
+        else *dst = v.x;
+    }
+}
+
+template <int P, int RS, bool DIFF, bool ADV>
+__global__ void __launch_bounds__(kWarp) dg_volume_kernel(const __grid_constant__ AsmArgs A) {
+    using DM = Dm<P, RS>;
+    using S = VolSmem<P, RS, DIFF, ADV>;
+    constexpr int QV = DM::QV;
+    extern __shared__ __align__(128) unsigned char sm[];
+    const int lane = threadIdx.x;
+    const int r = blockIdx.x;
+    const int t0 = A.g.vround_tri0[r];
+    const int n = A.g.vround_tri0[r + 1] - t0;
+    const bool has_c = A.c.vol_c != nullptr, has_f = A.c.vol_f != nullptr;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + S::OBAR);
+    // 8-byte sample arrays: the round's range is widened to 16-byte boundaries, the data then starts hc / hf bytes in
+    const size_t first = (size_t)QV * t0;
+    const uintptr_t pc = reinterpret_cast<uintptr_t>(A.c.vol_c + first), pf = reinterpret_cast<uintptr_t>(A.c.vol_f + first);
+    const int hc = has_c ? (int)(pc & 15) : 0, hf = has_f ? (int)(pf & 15) : 0;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        const uint32_t cnt = (uint32_t)(QV * n);
+        const uint32_t ba = DIFF ? cnt * 32 : 0, bb = ADV ? cnt * 16 : 0;
+        const uint32_t bc = has_c ? (hc + cnt * 8 + 15) & ~15u : 0, bf = has_f ? (hf + cnt * 8 + 15) & ~15u : 0;
+        const uint32_t bxy = (uint32_t)n * 48;
+        mbar_expect_tx(bar, ba + bb + bc + bf + bxy);
+        bulk_g2s(sm + S::OXY, A.g.tri_xy + 6 * (size_t)t0, bxy, bar);
+        if (DIFF) bulk_g2s(sm + S::OA, A.c.vol_a + 4 * first, ba, bar);
+        if (ADV) bulk_g2s(sm + S::OB, A.c.vol_b + 2 * first, bb, bar);
+        if (has_c) bulk_g2s(sm + S::OC, reinterpret_cast<const void*>(pc - hc), bc, bar);
+        if (has_f) bulk_g2s(sm + S::OF, reinterpret_cast<const void*>(pf - hf), bf, bar);
+    }
+    __syncwarp();
+    const bool active = lane < n;
+    const int t = t0 + (active ? lane : 0);
+    const int e = A.g.tri_elem[t];
+    const int seg = A.g.tri_seg ? A.g.tri_seg[t] : e;
+    const ElemBox bx = A.ebox[e];
+    // segments (= elements, or pieces of an element with more than 32 triangles) of the round
+    const int prev = __shfl_up_sync(kFull, seg, 1);
+    const bool head = active && (lane == 0 || seg != prev);
+    const unsigned hm = __ballot_sync(kFull, head);
+    const int nseg = __popc(hm);
+    {
+        int* s_start = reinterpret_cast<int*>(sm + S::OMETA);
+        int* s_seg = s_start + 36;
+        if (head) {
+            const int rank = __popc(hm & lanemask_lt());
+            s_start[rank] = lane;
+            s_seg[rank] = seg;
+        }
+        if (lane == 0) s_start[nseg] = n;
+    }
+    mbar_wait(bar, 0);
+    const int la = active ? lane : 0;
+    const double2 V0 = *reinterpret_cast<const double2*>(sm + S::OXY + la * 48);
+    const double2 V1 = *reinterpret_cast<const double2*>(sm + S::OXY + la * 48 + 16);
+    const double2 V2 = *reinterpret_cast<const double2*>(sm + S::OXY + la * 48 + 32);
+    // |det(0.5*[V1-V0; V2-V0])| (full_assembly.py:40-41); the extra 0.5 is the `0.5 * z` of :75-77
+    const double e1x = 0.5 * (V1.x - V0.x), e1y = 0.5 * (V1.y - V0.y);
+    const double e2x = 0.5 * (V2.x - V0.x), e2y = 0.5 * (V2.y - V0.y);
+    const double hdet = 0.5 * fabs(e1x * e2y - e1y * e2x);
+    volume_part<P, RS, 0, DIFF, ADV>(A, sm, lane, n, hc, hf, active, bx, V0, V1, V2, hdet, has_c, has_f, nseg);
+    if (RS > 1) volume_part<P, RS, RS - 1, DIFF, ADV>(A, sm, lane, n, hc, hf, active, bx, V0, V1, V2, hdet, has_c, has_f, nseg);
+}
+
+// =======================================================================================================================
+// face kernel
+// =======================================================================================================================
+template <int P, int RS, bool DIFF, bool ADV>
+struct FaceSmem {
+    using DM = Dm<P, RS>;
+    static constexpr int NPL = 8 + 3 * DM::QE;                  // 16-byte planes per item: record 4, neighbour box 4, a 2/point, b 1/point
+    static constexpr int PLANES = NPL * 512;
+    static constexpr int OOWN = PLANES;                          // own boxes of the round's elements [kMaxE][64 bytes]
+    static constexpr int OVD = OOWN + kMaxE * 64;                // volume sums of the round's segments [kMaxSeg][NV]
+    static constexpr int STAGE = OVD + kMaxSeg * DM::NV * 8;     // one staging buffer
+    static constexpr int OOUT = 2 * STAGE;                       // block rows of the round (+ 16 bytes of alignment shift)
+    static constexpr int OUTB = (32 + kMaxE) * DM::DD * 8 + 16;
+    static constexpr int NPQ = (DM::NB + 1) / 2;                 // pairs of one diagonal partial
+    static constexpr int PARTB = NPQ * kPartStride * 16;
+    // one pass: the diagonal partials use the (still empty) row buffer; several passes: a buffer of their own
+    static constexpr int OPART = RS == 1 ? OOUT : OOUT + OUTB;
+    static constexpr int OMETA = (RS == 1 ? (OOUT + (OUTB > PARTB ? OUTB : PARTB)) : (OPART + PARTB)) + 0;
+    static constexpr int TOTAL = OMETA + 4 * 96;
+    static_assert(STAGE % 16 == 0 && OUTB % 16 == 0 && PARTB % 16 == 0, "alignment");
+};
+
+struct FaceGeo {
+    double midx, midy, tanx, tany, nx, ny, De, sigma;
+};
+
+struct RoundExt {
+    int e0, ne, k0, k1, g0, g1, sg0, nsg;   // elements [e0,e0+ne), items [k0,k1), neighbour groups [g0,g1), volume segments [sg0,sg0+nsg)
+    int off, goff, sg;                      // lane i <= ne: adj_off / grp_off / first segment of element e0+i
+};
+
+__device__ __forceinline__ int seg0_of(const AsmArgs& A, int e) { return A.g.elem_seg0 ? A.g.elem_seg0[e] : e; }
+
+__device__ __forceinline__ RoundExt round_extent(const AsmArgs& A, int e0, int e_end, int lane) {
+    RoundExt x;
+    x.e0 = e0;
+    const int idx = e0 + lane;
+    const bool in = idx <= e_end && lane <= kMaxE;
+    x.off = in ? A.adj_off[idx] : 0;
+    x.goff = in ? A.grp_off[idx] : 0;
+    x.sg = in ? seg0_of(A, idx) : 0;
+    x.k0 = __shfl_sync(kFull, x.off, 0);
+    x.g0 = __shfl_sync(kFull, x.goff, 0);
+    x.sg0 = __shfl_sync(kFull, x.sg, 0);
+    // element i of the round is taken while the items fit one warp and the segments fit the staging buffer
+    const bool ok = in && lane >= 1 && (x.off - x.k0 <= kWarp) && (x.sg - x.sg0 <= kMaxSeg);
+    const unsigned m = __ballot_sync(kFull, ok) >> 1;
+    x.ne = __ffs(~m) - 1;                   // length of the run of set bits (both conditions are monotone)
+    if (x.ne == 0) __trap();                // an element with more than 32 items / kMaxSeg segments: rejected by the host entry
+    x.k1 = __shfl_sync(kFull, x.off, x.ne);
+    x.g1 = __shfl_sync(kFull, x.goff, x.ne);
+    x.nsg = __shfl_sync(kFull, x.sg, x.ne) - x.sg0;
+    return x;
+}
+
+struct ItemRegs {
+    int item, nbr;
+    unsigned char upw;
+};
+
+// cp.async staging of one round into buffer `sb` (everything an item needs, copied once)
+template <int P, int RS, bool DIFF, bool ADV>
+__device__ __forceinline__ ItemRegs stage_round(const AsmArgs& A, unsigned char* __restrict__ sb, const RoundExt& x, int lane) {
+    using DM = Dm<P, RS>;
+    using S = FaceSmem<P, RS, DIFF, ADV>;
+    constexpr int QE = DM::QE;
+    ItemRegs it;
+    it.item = 0; it.nbr = 0; it.upw = 0;
+    const size_t F = (size_t)A.g.n_iface;
+    if (lane < x.k1 - x.k0) {
+        it.item = A.adj_item[x.k0 + lane];
+        it.nbr = A.adj_nb[x.k0 + lane];
+        const int f = (it.item & 0x7fffffff) >> 1;
+        if (A.c.if_upwind) it.upw = A.c.if_upwind[f];
+        unsigned char* dst = sb + lane * 16;
+        const double2* rec = reinterpret_cast<const double2*>(A.frec + f);
+        const double2* box = reinterpret_cast<const double2*>(A.ebox + it.nbr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __pipeline_memcpy_async(dst + k * 512, rec + k, 16);
+            __pipeline_memcpy_async(dst + (4 + k) * 512, box + k, 16);
+        }
+#pragma unroll
+        for (int q = 0; q < QE; ++q) {
+            const size_t m = (size_t)q * F + f;
+            if (DIFF) {
+                __pipeline_memcpy_async(dst + (8 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m, 16);
+                __pipeline_memcpy_async(dst + (9 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m + 1, 16);
+            }
+            if (ADV) __pipeline_memcpy_async(dst + (8 + 2 * QE + q) * 512, reinterpret_cast<const double2*>(A.c.if_b) + m, 16);
+        }
+    }
+    if (lane < x.ne) {
+        const double2* box = reinterpret_cast<const double2*>(A.ebox + x.e0 + lane);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(sb + S::OOWN + lane * 64 + k * 16, box + k, 16);
+    }
+    {
+        const int pieces = x.nsg * (DM::NV / 2);
+        const double2* src = reinterpret_cast<const double2*>(A.vdiag + (size_t)x.sg0 * DM::NV);
+        for (int w = lane; w < pieces; w += kWarp) __pipeline_memcpy_async(sb + S::OVD + w * 16, src + w, 16);
+    }
+    return it;
+}
+
+__device__ __forceinline__ ElemBox lds_box(const unsigned char* p, int stride) {
+    const double2 m = *reinterpret_cast<const double2*>(p), ih = *reinterpret_cast<const double2*>(p + stride);
+    const double2 s05 = *reinterpret_cast<const double2*>(p + 2 * stride), s15 = *reinterpret_cast<const double2*>(p + 3 * stride);
+    ElemBox b;
+    b.mx = m.x; b.my = m.y; b.ihx = ih.x; b.ihy = ih.y; b.s05x = s05.x; b.s05y = s05.y; b.s15x = s15.x; b.s15y = s15.y;
+    return b;
+}
+
+// One pass over the face points of the lane's item: rows [J0, J0+RJ) of the diagonal (OFF = false: columns = basis of the
+// element) or off-diagonal block (OFF = true: columns = basis of the neighbour).
+//   P_r = s phi_r, Q_r = -F_r/2, V_c = W s phi_c, U_c = (sigma + gamma) V_c - W F_c/2;  B[r,c] += P_r U_c + Q_r V_c
+// (full_assembly.py:174-212; s = +1 on the K1 side, -1 on the K2 side).
+template <int P, int RS, int PART, bool DIFF, bool ADV, bool OFF>
+__device__ __forceinline__ void face_pass(const AsmArgs& A, const unsigned char* __restrict__ sb, int lane, const FaceGeo& g,
+                                          double sgn, bool down, const ElemBox& bxe, const ElemBox& bxo,
+                                          double* __restrict__ acc) {
+    using DM = Dm<P, RS>;
+    constexpr int D = DM::D, RJ = DM::RJ, QE = DM::QE, J0 = PART * RJ;
+#pragma unroll 1
+    for (int q = 0; q < QE; ++q) {
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
+        if (DIFF) {
+            const double2 r0 = *reinterpret_cast<const double2*>(sb + (8 + 2 * q) * 512 + lane * 16);
+            const double2 r1 = *reinterpret_cast<const double2*>(sb + (9 + 2 * q) * 512 + lane * 16);
+            a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
+        }
+        if (ADV) {
+            const double2 bb = *reinterpret_cast<const double2*>(sb + (8 + 2 * QE + q) * 512 + lane * 16);
+            b0 = bb.x; b1 = bb.y;
+        }
+        const double x = g.midx + A.xe[q] * g.tanx;
+        const double y = g.midy + A.xe[q] * g.tany;
+        const double W = g.De * A.we[q];
+        double atn0 = 0, atn1 = 0, gamma = 0;
+        if (DIFF) {
+            // F_k = n . (a grad phi_k) = (a^T n) . grad phi_k
+            atn0 = g.nx * a00 + g.ny * a10;
+            atn1 = g.nx * a01 + g.ny * a11;
+        }
+        if (ADV) {
+            const double beta = b0 * g.nx + b1 * g.ny;
+            gamma = down ? -sgn * beta : 0.0;
+        }
+        const double hw0 = -0.5 * W * atn0, hw1 = -0.5 * W * atn1;     // -W/2 * a^T n
+        const double sg = g.sigma + gamma;
+        double phi[D], gx[D], gy[D];
+        eval_basis<P, DIFF>(x, y, bxe, A.lc, phi, gx, gy);
+        double Pr[RJ], Qr[RJ];
+#pragma unroll
+        for (int jj = 0; jj < RJ; ++jj) {
+            const int j = J0 + jj;
+            Pr[jj] = sgn * phi[j];
+            Qr[jj] = 0.0;
+            if (DIFF) {
+                if (gx_nz<P>(j) && gy_nz<P>(j)) Qr[jj] = -0.5 * (atn0 * gx[j] + atn1 * gy[j]);
+                else if (gx_nz<P>(j)) Qr[jj] = -0.5 * (atn0 * gx[j]);
+                else if (gy_nz<P>(j)) Qr[jj] = -0.5 * (atn1 * gy[j]);
+            }
+        }
+        const double Ws = OFF ? -(W * sgn) : W * sgn;
+        if (OFF) eval_basis<P, DIFF>(x, y, bxo, A.lc, phi, gx, gy);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const double Vc = Ws * phi[i];
+            double Uc = sg * Vc;
+            if (DIFF && gy_nz<P>(i)) Uc = fma(hw1, gy[i], Uc);
+            if (DIFF && gx_nz<P>(i)) Uc = fma(hw0, gx[i], Uc);
+#pragma unroll
+            for (int jj = 0; jj < RJ; ++jj) {
+                const int j = J0 + jj;
+                double v = acc[jj * D + i];
+                v = fma(Pr[jj], Uc, v);
+                if (DIFF && (gx_nz<P>(j) || gy_nz<P>(j))) v = fma(Qr[jj], Vc, v);
+                acc[jj * D + i] = v;
+            }
+        }
+    }
+}
+
+// per-lane view of the round
+struct LaneCtx {
+    bool active, headf;
+    int el;          // element of the item inside the round
+    int slot;        // block column slot of the off-diagonal block in its row
+    int ro, rowlen;  // first double of the element's rows in the row buffer, doubles per scalar row
+    int depth;       // 0 = first item of its neighbour group, k = k-th repeat of the same neighbour
+    double sgn;
+    bool down;
+};
+
+template <int P, int RS, int PART, bool DIFF, bool ADV>
+__device__ __forceinline__ void diag_part(const AsmArgs& A, unsigned char* __restrict__ sm, const unsigned char* __restrict__ sb,
+                                          int lane, const RoundExt& x, const LaneCtx& c, const FaceGeo& g, const ElemBox& bxe,
+                                          double* __restrict__ outd, int maxdepth, unsigned& zeros) {
+    using DM = Dm<P, RS>;
+    using S = FaceSmem<P, RS, DIFF, ADV>;
+    constexpr int D = DM::D, DD = DM::DD, NB = DM::NB, NV = DM::NV;
+    constexpr bool LAST = PART == RS - 1;
+    constexpr int NPQ = S::NPQ;                                               // face partial pairs
+    constexpr int NPR = RS == 1 ? NV / 2 : NB / 2 + (LAST ? D / 2 : 0);       // pairs reduced per element in this part
+    constexpr int NIT = (kMaxE * NPR + kWarp - 1) / kWarp;
+    double acc[2 * NPQ];
+#pragma unroll
+    for (int v = 0; v < 2 * NPQ; ++v) acc[v] = 0.0;
+    if (c.active) face_pass<P, RS, PART, DIFF, ADV, false>(A, sb, lane, g, c.sgn, c.down, bxe, bxe, acc);
+    double2* part = reinterpret_cast<double2*>(sm + S::OPART);
+    if (RS == 1 || PART == 0) {
+        if (lane == 0) bulk_wait_read();            // the previous round's bulk store has read the row buffer
+    }
+    __syncwarp();
+    if (c.active) {
+#pragma unroll
+        for (int kk = 0; kk < NPQ; ++kk) part[kk * kPartStride + lane] = make_double2(acc[2 * kk], acc[2 * kk + 1]);
+    }
+    __syncwarp();
+    const int* s_ls = reinterpret_cast<const int*>(sm + S::OMETA);            // [kMaxE+1] first lane of every element
+    const int* s_ro = s_ls + 16;                                              // [kMaxE]
+    const int* s_rowlen = s_ro + 16;
+    const int* s_dslot = s_rowlen + 16;
+    const int* s_sg = s_dslot + 16;                                           // [kMaxE+1] first staged segment of every element
+    const double* vd = reinterpret_cast<const double*>(sb + S::OVD);
+    double2 res[NIT];
+    const int total = x.ne * NPR;
+#pragma unroll
+    for (int itn = 0; itn < NIT; ++itn) {
+        const int w = lane + itn * kWarp;
+        res[itn] = make_double2(0.0, 0.0);
+        if (w < total) {
+            const int el = w / NPR, kk = w - el * NPR;
+            const int vi = pair_dst<P, RS, PART>(kk);
+            // volume sums first (triangles, main.py:315), then the faces in item order
+            double2 v = make_double2(0.0, 0.0);
+            for (int s = s_sg[el]; s < s_sg[el + 1]; ++s) {
+                const double2 t = *reinterpret_cast<const double2*>(vd + (size_t)s * NV + vi);
+                v.x += t.x;
+                v.y += t.y;
+            }
+            if (2 * kk < NB) {
+                const int l0 = s_ls[el], l1 = s_ls[el + 1];
+                for (int l = l0; l < l1; ++l) {
+                    const double2 t = part[kk * kPartStride + l];
+                    v.x += t.x;
+                    v.y += t.y;
+                }
+            }
+            res[itn] = v;
+        }
+    }
+    __syncwarp();                                   // all partials are read: the row buffer may be written (RS == 1 alias)
+#pragma unroll
+    for (int itn = 0; itn < NIT; ++itn) {
+        const int w = lane + itn * kWarp;
+        if (w < total) {
+            const int el = w / NPR, kk = w - el * NPR;
+            const int vi = pair_dst<P, RS, PART>(kk);
+            const int e = x.e0 + el;
+            const int ro = s_ro[el], rowlen = s_rowlen[el], ds = s_dslot[el];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int v = vi + h;
+                const double val = h ? res[itn].y : res[itn].x;
+                if (v < DD) {
+                    outd[ro + (v / D) * rowlen + ds * D + (v % D)] = val;
+                    if (maxdepth == 0) zeros += (val == 0.0);
+                } else if (v < NV) {
+                    A.load[(size_t)e * D + (v - DD)] = val;
+                }
+            }
+        }
+    }
+}
+
+template <int P, int RS, int PART, bool DIFF, bool ADV>
+__device__ __forceinline__ void off_part(const AsmArgs& A, const unsigned char* __restrict__ sb, int lane, const LaneCtx& c,
+                                         const FaceGeo& g, const ElemBox& bxe, const ElemBox& bxo, double* __restrict__ outd,
+                                         int maxdepth, unsigned& zeros) {
+    using DM = Dm<P, RS>;
+    constexpr int D = DM::D, RJ = DM::RJ, NB = DM::NB, J0 = PART * RJ;
+    double acc[NB];
+#pragma unroll
+    for (int v = 0; v < NB; ++v) acc[v] = 0.0;
+    if (c.active) face_pass<P, RS, PART, DIFF, ADV, true>(A, sb, lane, g, c.sgn, c.down, bxe, bxo, acc);
+    double* dst0 = outd + c.ro + c.slot * D;
+    if (c.active && c.depth == 0) {
+#pragma unroll
+        for (int jj = 0; jj < RJ; ++jj) {
+            double* dst = dst0 + (J0 + jj) * c.rowlen;
+            if ((D & 1) == 0) {
+#pragma unroll
+                for (int i = 0; i < D; i += 2) reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(acc[jj * D + i], acc[jj * D + i + 1]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < D; ++i) dst[i] = acc[jj * D + i];
+            }
+        }
+        if (maxdepth == 0) {
+#pragma unroll
+            for (int v = 0; v < NB; ++v) zeros += (acc[v] == 0.0);
+        }
+    }
+    // faces that repeat the previous neighbour add to its block, in item order
+    for (int dd = 1; dd <= maxdepth; ++dd) {
+        __syncwarp();
+        if (c.active && c.depth == dd) {
+#pragma unroll
+            for (int jj = 0; jj < RJ; ++jj) {
+                double* dst = dst0 + (J0 + jj) * c.rowlen;
+#pragma unroll
+                for (int i = 0; i < D; ++i) dst[i] += acc[jj * D + i];
+            }
+        }
+    }
+}
+
+template <int P, int RS, bool DIFF, bool ADV>
+__global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ AsmArgs A) {
+    using DM = Dm<P, RS>;
+    using S = FaceSmem<P, RS, DIFF, ADV>;
+    constexpr int D = DM::D, DD = DM::DD;
+    extern __shared__ __align__(128) unsigned char sm[];
+    const int lane = threadIdx.x;
+    const int e_beg = blockIdx.x * kWindow;
+    const int e_end = min(e_beg + kWindow, A.g.n_rows);
+    unsigned zeros = 0;
+    int* s_ls = reinterpret_cast<int*>(sm + S::OMETA);
+    int* s_ro = s_ls + 16;
+    int* s_rowlen = s_ro + 16;
+    int* s_dslot = s_rowlen + 16;
+    int* s_sg = s_dslot + 16;
+
+    RoundExt x = round_extent(A, e_beg, e_end, lane);
+    ItemRegs it = stage_round<P, RS, DIFF, ADV>(A, sm, x, lane);
+    __pipeline_commit();
+    int buf = 0;
+    while (true) {
+        const int e_next = x.e0 + x.ne;
+        const bool has_next = e_next < e_end;
+        RoundExt xn = x;
+        ItemRegs itn = it;
+        if (has_next) {
+            xn = round_extent(A, e_next, e_end, lane);
+            itn = stage_round<P, RS, DIFF, ADV>(A, sm + (buf ^ 1) * S::STAGE, xn, lane);
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(1);
+        __syncwarp();
+        const unsigned char* sb = sm + buf * S::STAGE;
+
+        // ---- decode the round ------------------------------------------------------------------------------------------
+        LaneCtx c;
+        const int nit = x.k1 - x.k0;
+        c.active = lane < nit;
+        const int k = x.k0 + lane;
+        c.el = 0;
+#pragma unroll
+        for (int i = 1; i < kMaxE; ++i) {
+            const int o = __shfl_sync(kFull, x.off, i);
+            if (i < x.ne && k >= o) ++c.el;
+        }
+        if (!c.active) c.el = 0;
+        const int e = x.e0 + c.el;
+        const int eg = gid_of(A, e);
+        const int og = c.active ? gid_of(A, it.nbr) : 0;
+        c.headf = c.active && it.item >= 0;
+        int gi = 0, my_dslot = 0;
+        unsigned my_heads = 0;
+        for (int i = 0; i < x.ne; ++i) {
+            const bool mine = c.active && c.el == i;
+            const unsigned hm = __ballot_sync(kFull, mine && c.headf);
+            const unsigned lm = __ballot_sync(kFull, mine && c.headf && og < eg);
+            if (mine) {
+                my_heads = hm & (lanemask_lt() | (1u << lane));
+                gi = __popc(my_heads) - 1;
+            }
+            if (lane == i) my_dslot = __popc(lm);
+        }
+        c.slot = gi + (og > eg ? 1 : 0);
+        c.depth = c.active ? lane - (31 - __clz(my_heads)) : 0;
+        const int maxdepth = A.has_dups ? __reduce_max_sync(kFull, c.depth) : 0;
+        // lane i <= ne: layout of element e0+i in the row buffer
+        const int goff_next = __shfl_down_sync(kFull, x.goff, 1);
+        const int my_ro = DD * ((x.goff - x.g0) + lane);
+        const int my_rowlen = (goff_next - x.goff + 1) * D;
+        if (lane <= x.ne) {
+            s_ls[lane] = x.off - x.k0;
+            s_sg[lane] = x.sg - x.sg0;
+        }
+        if (lane < x.ne) {
+            s_ro[lane] = my_ro;
+            s_rowlen[lane] = my_rowlen;
+            s_dslot[lane] = my_dslot;
+        }
+        c.ro = __shfl_sync(kFull, my_ro, c.el);
+        c.rowlen = __shfl_sync(kFull, my_rowlen, c.el);
+        const int side = it.item & 1;
+        c.sgn = side ? -1.0 : 1.0;
+        c.down = A.c.if_upwind ? ((it.upw != 0) == (side == 1)) : false;
+        FaceGeo g;
+        {
+            const unsigned char* p = sb + lane * 16;
+            const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 512);
+            const double2 cc = *reinterpret_cast<const double2*>(p + 1024), d = *reinterpret_cast<const double2*>(p + 1536);
+            g.midx = a.x; g.midy = a.y; g.tanx = b.x; g.tany = b.y; g.nx = cc.x; g.ny = cc.y; g.De = d.x; g.sigma = d.y;
+        }
+        const ElemBox bxe = lds_box(sb + S::OOWN + c.el * 64, 16);
+        const ElemBox bxo = lds_box(sb + 4 * 512 + lane * 16, 512);
+        // first byte of the round's rows in the value array; the row buffer starts at the same 16-byte phase
+        double* gdst = A.data + (size_t)DD * ((size_t)x.g0 + x.e0);
+        const int oshift = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
+        double* outd = reinterpret_cast<double*>(sm + S::OOUT + oshift);
+
+        // ---- diagonal contributions: per-lane partial -> ordered per-element sum -> diagonal block, load --------------------
+        diag_part<P, RS, 0, DIFF, ADV>(A, sm, sb, lane, x, c, g, bxe, outd, maxdepth, zeros);
+        if (RS > 1) diag_part<P, RS, RS - 1, DIFF, ADV>(A, sm, sb, lane, x, c, g, bxe, outd, maxdepth, zeros);
+        // ---- off-diagonal blocks ------------------------------------------------------------------------------------------
+        off_part<P, RS, 0, DIFF, ADV>(A, sb, lane, c, g, bxe, bxo, outd, maxdepth, zeros);
+        if (RS > 1) off_part<P, RS, RS - 1, DIFF, ADV>(A, sb, lane, c, g, bxe, bxo, outd, maxdepth, zeros);
+        __syncwarp();
+        const int ndbl = DD * ((x.g1 - x.g0) + x.ne);      // doubles of the round's rows
+        if (maxdepth > 0) {
+            // merged blocks: count the exact zeros of the finished rows (the per-lane counts above were skipped)
+            for (int w = lane; w < ndbl; w += kWarp) zeros += (outd[w] == 0.0);
+        }
+        // ---- one bulk store for all rows of the round ---------------------------------------------------------------------------
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            int lo = 0, n = ndbl;
+            if (oshift) { gdst[0] = outd[0]; lo = 1; --n; }
+            const int core = n & ~1;
+            if (core) bulk_s2g(gdst + lo, outd + lo, (uint32_t)core * 8);
+            if (n & 1) gdst[lo + core] = outd[lo + core];
+        }
+        if (!has_next) break;
+        x = xn;
+        it = itn;
+        buf ^= 1;
+    }
+    if (lane == 0) bulk_wait_read();
+    if (zeros) atomicAdd(A.zero_count, (unsigned long long)zeros);
+}
+
+// =======================================================================================================================
+template <int P, int RS, bool DIFF, bool ADV>
+static int launch(const AsmArgs& A, cudaStream_t st) {
+    using VS = VolSmem<P, RS, DIFF, ADV>;
+    using FS = FaceSmem<P, RS, DIFF, ADV>;
+    auto vk = dg_volume_kernel<P, RS, DIFF, ADV>;
+    auto fk = dg_face_kernel<P, RS, DIFF, ADV>;
+    RB_CUDA(cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS::TOTAL));
+    RB_CUDA(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS::TOTAL));
+    if (A.g.n_vrounds > 0) {
+        vk<<<A.g.n_vrounds, kWarp, VS::TOTAL, st>>>(A);
+        RB_LAUNCH_CHECK("dg_volume_kernel");
+    }
+    const int blocks = (int)div_up(A.g.n_rows, kWindow);
+    fk<<<blocks, kWarp, FS::TOTAL, st>>>(A);
+    RB_LAUNCH_CHECK("dg_face_kernel");
+    return 0;
+}
+
+template <int P, int RS>
+static int dispatch(const AsmArgs& A, bool diff, bool adv, cudaStream_t st) {
+    if (diff && adv) return launch<P, RS, true, true>(A, st);
+    if (diff) return launch<P, RS, true, false>(A, st);
+    return launch<P, RS, false, true>(A, st);
+}
+
+}  // namespace items
+
+int items_max_face_items() { return items::kWarp; }
+int items_max_segments() { return items::kMaxSeg; }
+
+int launch_assemble_items(const AsmArgs& A, int p, bool diff, bool adv, cudaStream_t st) {
+    switch (p) {
+        case 1: return items::dispatch<1, 1>(A, diff, adv, st);
+        case 2: return items::dispatch<2, 1>(A, diff, adv, st);
+        default: return items::dispatch<3, 2>(A, diff, adv, st);
+    }
+}
+
+}  // namespace rb

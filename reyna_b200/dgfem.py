@@ -191,13 +191,16 @@ class DGFEM:
             nonlocal nbytes
             if X.shape[0] == 0:
                 return
-            buf = self._staging(torch, key, (X.shape[0],) + tail)
-            sampling.evaluate_batched(fn, X, tail, out=buf.numpy())
-            dev_t[key] = buf.to(dev, non_blocking=True)
-            nbytes += buf.numel() * 8
+            M = X.shape[0]
+            # one spare row: the volume kernel's bulk copies move 16-byte units (rb_coefs, include/reyna_b200.h)
+            buf = self._staging(torch, key, (M + 1,) + tail)
+            sampling.evaluate_batched(fn, X, tail, out=buf.numpy()[:M])
+            buf.numpy()[M] = 0.0
+            dev_t[key] = buf.to(dev, non_blocking=True)[:M]
+            nbytes += M * int(np.prod(tail, dtype=np.int64)) * 8
 
         pts = sampling.cached_points(self.geometry, fg, self.element_reference_quadrature, self.edge_reference_quadrature)
-        Xv = pts['Xv']
+        Xv = pts['Xs']                 # round order of reyna_b200.stream (what dg_volume_kernel reads)
         if self.diffusion is not None:
             put('vol_a', self.diffusion, Xv, (2, 2))
         if self.advection is not None:
@@ -273,6 +276,10 @@ class DGFEM:
             cache[key] = {n: torch.from_numpy(getattr(fg, n)).to(dev) for n in names}
             gid = getattr(fg, 'elem_gid', None)      # partitions only: local -> global element id
             cache[key]['elem_gid'] = torch.from_numpy(gid).to(dev) if gid is not None else None
+            vs = sampling.volume_stream_of(fg)       # volume rounds of dg_volume_kernel
+            for n in ('tri_xy', 'vround_tri0', 'tri_seg', 'elem_seg0'):
+                a = getattr(vs, n)
+                cache[key][n] = torch.from_numpy(a).to(dev) if a is not None else None
         return cache[key]
 
     def _quad_struct(self) -> "_lib.RbQuad":
@@ -330,8 +337,9 @@ class DGFEM:
         i32 = dict(dtype=torch.int32, device=dev)
         f64 = dict(dtype=torch.float64, device=dev)
 
+        vs = sampling.volume_stream_of(fg)
         g = _lib.RbGeom(n_nodes=fg.n_nodes, n_elem=E, n_rows=R, n_tri=fg.n_tri, n_iface=fg.n_iface, n_bface=fg.n_bface,
-                        **{k: _ptr(v) for k, v in gd.items()})
+                        n_vrounds=vs.n_rounds, n_vsegs=vs.n_segs, **{k: _ptr(v) for k, v in gd.items()})
         co = _lib.RbCoefs(**{k: _ptr(cd.get(k)) for k in ('vol_a', 'vol_b', 'vol_c', 'vol_f', 'if_a', 'if_b', 'if_a_mid',
                                                           'if_upwind', 'bf_a', 'bf_b', 'bf_g', 'bf_a_mid')})
         q = self._quad_struct()
@@ -371,7 +379,7 @@ class DGFEM:
                                             C.c_void_p(side.cuda_stream)), 'reyna_b200_csr_pattern')
         indptr.record_stream(side)
         indices.record_stream(side)
-        aws_bytes = L.reyna_b200_assemble_workspace(E, fg.n_iface)
+        aws_bytes = L.reyna_b200_assemble_workspace(E, fg.n_iface, vs.n_segs, p)
         aws = torch.empty(aws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(L.reyna_b200_assemble(C.byref(g), C.byref(st), C.byref(co), C.byref(q), float(self.sigma_D),
                                          _ptr(data), _ptr(load), _ptr(zero_count), _ptr(aws), aws_bytes, sp),

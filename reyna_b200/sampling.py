@@ -3,7 +3,7 @@
 The reference calls every coefficient callable once per sub-triangle / face on (p+1)^2 or p+1 points
 (full_assembly.py:57,65,69,73,140,159,194-195; boundary_assembly.py:44-45,103,111-112).  Here the points of all items
 are generated with exactly the reference's formulas (assembly_aux.py:7-29 for triangles, ``mid + x_q * tanvec`` for
-edges, full_assembly.py:118-121), laid out q-major (``[q][item]``, the layout the kernels read coalesced), and each
+edges, full_assembly.py:118-121), laid out q-major (``[q][item]``; volume points in the round order of ``reyna_b200.stream``), and each
 callable is evaluated once over the whole array -- in row chunks on a thread pool, because the numba-compiled callables
 are ``nogil`` and element-wise, so chunking does not change a single bit of the result.
 """
@@ -92,6 +92,34 @@ def _edge_points_kernel(nodes, edges, x1, mid, out):
             out[q, f, 1] = x1[q] * ty + my
 
 
+@njit(parallel=True, cache=True, nogil=True)
+def _volume_stream_points_kernel(nodes, tri, ref2, tri_t0, tri_n, out):
+    Q, T = ref2.shape[0], tri.shape[0]
+    for t in prange(T):
+        i0, i1, i2 = tri[t, 0], tri[t, 1], tri[t, 2]
+        x0, y0 = nodes[i0, 0], nodes[i0, 1]
+        x1, y1 = nodes[i1, 0], nodes[i1, 1]
+        x2, y2 = nodes[i2, 0], nodes[i2, 1]
+        n = tri_n[t]
+        base = tri_t0[t] * Q + (t - tri_t0[t])
+        for q in range(Q):
+            r0, r1 = ref2[q, 0], ref2[q, 1]
+            l0 = 1.0 - r0 - r1
+            out[base + q * n, 0] = l0 * x0 + r0 * x1 + r1 * x2
+            out[base + q * n, 1] = l0 * y0 + r0 * y1 + r1 * y2
+
+
+def volume_stream_points(fg, vs, ref2: np.ndarray) -> np.ndarray:
+    """(Qv*T, 2) physical volume points in the round order of ``reyna_b200.stream`` (the order of the volume samples of
+    ``rb_coefs``); same formula as ``volume_points``: X = (1-r0-r1) V0 + r0 V1 + r1 V2 (assembly_aux.py:7-29)."""
+    ref2 = np.ascontiguousarray(ref2, dtype=np.float64)
+    Q = ref2.shape[0]
+    out = np.empty((fg.n_tri * Q, 2))
+    _set_numba_threads()
+    _volume_stream_points_kernel(fg.nodes, fg.tri, ref2, vs.tri_t0, vs.tri_n, out)
+    return out
+
+
 def volume_points(fg, ref2: np.ndarray) -> np.ndarray:
     """(Qv*T, 2) physical volume points, q-major: X[q,t] = (1-r0-r1) V0 + r0 V1 + r1 V2 (assembly_aux.py:7-29)."""
     ref2 = np.ascontiguousarray(ref2, dtype=np.float64)
@@ -118,8 +146,34 @@ def _set_numba_threads() -> None:
         numba.set_num_threads(n)
 
 
+def volume_stream_of(fg):
+    """The volume-round tables of a flat geometry (``reyna_b200.stream.volume_stream``), cached on it."""
+    vs = getattr(fg, '_vs', None)
+    if vs is None:
+        from .stream import volume_stream
+        vs = volume_stream(fg)
+        fg._vs = vs
+    return vs
+
+
+class _LazyPoints(dict):
+    """Point cache of one quadrature rule; the q-major volume points ``Xv`` (only ``errors()`` reads them) are generated on
+    first use."""
+
+    def __init__(self, fg, ref2):
+        super().__init__()
+        self._fg, self._ref2 = fg, ref2
+
+    def __missing__(self, key):
+        if key != 'Xv':
+            raise KeyError(key)
+        self['Xv'] = volume_points(self._fg, self._ref2)
+        return self['Xv']
+
+
 def cached_points(geometry, fg, element_rule, edge_rule) -> dict:
-    """Physical quadrature points of a geometry for one quadrature rule: volume ``Xv``, interior faces ``(mid_i, Xi)``,
+    """Physical quadrature points of a geometry for one quadrature rule: volume ``Xs`` (round order, what the assembly
+    samples) and ``Xv`` (q-major, lazily, for ``errors()``), interior faces ``(mid_i, Xi)``,
     boundary faces ``(mid_b, Xb)``.  They depend on the mesh and the polynomial degree only, so they are computed once
     and kept on the geometry object (repeated assemblies with changing coefficients pay for the callables only)."""
     ref2 = np.asarray(element_rule[1])
@@ -134,7 +188,8 @@ def cached_points(geometry, fg, element_rule, edge_rule) -> dict:
             pass
     pts = cache.get(key)
     if pts is None:
-        pts = {'Xv': volume_points(fg, ref2)}
+        pts = _LazyPoints(fg, ref2)
+        pts['Xs'] = volume_stream_points(fg, volume_stream_of(fg), ref2)
         pts['mid_i'], pts['Xi'] = edge_points(fg.nodes, fg.iedge, x1) if fg.n_iface else (np.zeros((0, 2)), np.zeros((0, 2)))
         pts['mid_b'], pts['Xb'] = edge_points(fg.nodes, fg.bedge, x1) if fg.n_bface else (np.zeros((0, 2)), np.zeros((0, 2)))
         cache[key] = pts

@@ -63,7 +63,8 @@ def test_ctypes_field_offsets_match_header():
     import tempfile
     from reyna_b200 import _lib
     structs = [("rb_mg_opts", _lib.RbMgOpts), ("rb_mg_dist", _lib.RbMgDist), ("rb_solve_opts", _lib.RbSolveOpts),
-               ("rb_solve_info", _lib.RbSolveInfo), ("rb_structure", _lib.RbStructure), ("rb_coefs", _lib.RbCoefs)]
+               ("rb_solve_info", _lib.RbSolveInfo), ("rb_structure", _lib.RbStructure), ("rb_coefs", _lib.RbCoefs),
+               ("rb_geom", _lib.RbGeom)]
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "o.c")
         with open(src, "w") as fh:

@@ -70,6 +70,9 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t 
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// CTA-wide barrier of the face kernel (64 threads); the two warps reach it from different code paths
+__device__ __forceinline__ void cta_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -120,8 +123,7 @@ struct VolSmem {
     static constexpr int PARTB = DM::NPAIR_MAX * kPartStride * 16;
     // one pass: the partial blocks overwrite the consumed samples; several passes: the samples have to survive
     static constexpr int OPART = RS == 1 ? 0 : SAMPLES;
-    static constexpr int OXY = RS == 1 ? ((SAMPLES > PARTB ? SAMPLES : PARTB) + 15) / 16 * 16 : SAMPLES + PARTB;
-    static constexpr int OMETA = OXY + 32 * 48;                          // int s_start[36], s_seg[36]
+    static constexpr int OMETA = RS == 1 ? ((SAMPLES > PARTB ? SAMPLES : PARTB) + 15) / 16 * 16 : SAMPLES + PARTB;   // int s_start[36], s_seg[36]
     static constexpr int OBAR = OMETA + 4 * 72;
     static constexpr int TOTAL = OBAR + 16;
 };
@@ -223,10 +225,15 @@ __device__ __forceinline__ void volume_part(const AsmArgs& A, unsigned char* __r
         const int s = w / NP, kk = w - s * NP;
         const int l0 = s_start[s], l1 = s_start[s + 1];
         double2 v = part[kk * kPartStride + l0];
-        for (int l = l0 + 1; l < l1; ++l) {         // triangles in order (main.py:315)
-            const double2 t = part[kk * kPartStride + l];
-            v.x += t.x;
-            v.y += t.y;
+        for (int l = l0 + 1; l < l1; l += 4) {      // triangles in order (main.py:315); four loads in flight (x + 0.0 = x)
+            double2 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = l + u < l1 ? part[kk * kPartStride + l + u] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v.x += t[u].x;
+                v.y += t[u].y;
+            }
         }
         double* dst = A.vdiag + (size_t)s_seg[s] * DM::NV + pair_dst<P, RS, PART>(kk);
         if (2 * kk + 1 < NVAL) *reinterpret_cast<double2*>(dst) = v;
@@ -235,7 +242,7 @@ __device__ __forceinline__ void volume_part(const AsmArgs& A, unsigned char* __r
 }
 
 template <int P, int RS, bool DIFF, bool ADV>
-__global__ void __launch_bounds__(kWarp) dg_volume_kernel(const __grid_constant__ AsmArgs A) {
+__global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const __grid_constant__ AsmArgs A) {
     using DM = Dm<P, RS>;
     using S = VolSmem<P, RS, DIFF, ADV>;
     constexpr int QV = DM::QV;
@@ -255,9 +262,7 @@ __global__ void __launch_bounds__(kWarp) dg_volume_kernel(const __grid_constant_
         const uint32_t cnt = (uint32_t)(QV * n);
         const uint32_t ba = DIFF ? cnt * 32 : 0, bb = ADV ? cnt * 16 : 0;
         const uint32_t bc = has_c ? (hc + cnt * 8 + 15) & ~15u : 0, bf = has_f ? (hf + cnt * 8 + 15) & ~15u : 0;
-        const uint32_t bxy = (uint32_t)n * 48;
-        mbar_expect_tx(bar, ba + bb + bc + bf + bxy);
-        bulk_g2s(sm + S::OXY, A.g.tri_xy + 6 * (size_t)t0, bxy, bar);
+        mbar_expect_tx(bar, ba + bb + bc + bf);
         if (DIFF) bulk_g2s(sm + S::OA, A.c.vol_a + 4 * first, ba, bar);
         if (ADV) bulk_g2s(sm + S::OB, A.c.vol_b + 2 * first, bb, bar);
         if (has_c) bulk_g2s(sm + S::OC, reinterpret_cast<const void*>(pc - hc), bc, bar);
@@ -269,6 +274,8 @@ __global__ void __launch_bounds__(kWarp) dg_volume_kernel(const __grid_constant_
     const int e = A.g.tri_elem[t];
     const int seg = A.g.tri_seg ? A.g.tri_seg[t] : e;
     const ElemBox bx = A.ebox[e];
+    const double2* xy = reinterpret_cast<const double2*>(A.g.tri_xy) + 3 * (size_t)t;
+    const double2 V0 = xy[0], V1 = xy[1], V2 = xy[2];
     // segments (= elements, or pieces of an element with more than 32 triangles) of the round
     const int prev = __shfl_up_sync(kFull, seg, 1);
     const bool head = active && (lane == 0 || seg != prev);
@@ -285,10 +292,6 @@ __global__ void __launch_bounds__(kWarp) dg_volume_kernel(const __grid_constant_
         if (lane == 0) s_start[nseg] = n;
     }
     mbar_wait(bar, 0);
-    const int la = active ? lane : 0;
-    const double2 V0 = *reinterpret_cast<const double2*>(sm + S::OXY + la * 48);
-    const double2 V1 = *reinterpret_cast<const double2*>(sm + S::OXY + la * 48 + 16);
-    const double2 V2 = *reinterpret_cast<const double2*>(sm + S::OXY + la * 48 + 32);
     // |det(0.5*[V1-V0; V2-V0])| (full_assembly.py:40-41); the extra 0.5 is the `0.5 * z` of :75-77
     const double e1x = 0.5 * (V1.x - V0.x), e1y = 0.5 * (V1.y - V0.y);
     const double e2x = 0.5 * (V2.x - V0.x), e2y = 0.5 * (V2.y - V0.y);
@@ -300,6 +303,9 @@ __global__ void __launch_bounds__(kWarp) dg_volume_kernel(const __grid_constant_
 // =======================================================================================================================
 // face kernel
 // =======================================================================================================================
+constexpr int kFaceThreads = 64;   // warp 0 ("D"): diagonal contributions + their ordered sums; warp 1 ("O"): off-diagonal blocks
+constexpr int kTab = 72;           // ints per window table (kWindow + 1 entries used)
+
 template <int P, int RS, bool DIFF, bool ADV>
 struct FaceSmem {
     using DM = Dm<P, RS>;
@@ -314,8 +320,8 @@ struct FaceSmem {
     static constexpr int PARTB = NPQ * kPartStride * 16;
     // one pass: the diagonal partials use the (still empty) row buffer; several passes: a buffer of their own
     static constexpr int OPART = RS == 1 ? OOUT : OOUT + OUTB;
-    static constexpr int OMETA = (RS == 1 ? (OOUT + (OUTB > PARTB ? OUTB : PARTB)) : (OPART + PARTB)) + 0;
-    static constexpr int TOTAL = OMETA + 4 * 96;
+    static constexpr int OWIN = RS == 1 ? (OOUT + (OUTB > PARTB ? OUTB : PARTB)) : (OPART + PARTB);
+    static constexpr int TOTAL = OWIN + 5 * kTab * 4;            // window tables: adj_off, grp_off, first segment, gid, rounds
     static_assert(STAGE % 16 == 0 && OUTB % 16 == 0 && PARTB % 16 == 0, "alignment");
 };
 
@@ -323,83 +329,92 @@ struct FaceGeo {
     double midx, midy, tanx, tany, nx, ny, De, sigma;
 };
 
-struct RoundExt {
-    int e0, ne, k0, k1, g0, g1, sg0, nsg;   // elements [e0,e0+ne), items [k0,k1), neighbour groups [g0,g1), volume segments [sg0,sg0+nsg)
-    int off, goff, sg;                      // lane i <= ne: adj_off / grp_off / first segment of element e0+i
+// a round: whole elements [e0, e0+ne) of the window (window-relative), their items [k0,k1), neighbour groups [g0,g1) and
+// volume segments [sg0, sg0+nsg); lane i <= ne also holds the table entries of element e0+i
+struct Round {
+    int e0, ne, k0, k1, g0, g1, sg0, nsg;
+    int off, goff, sg;
 };
 
-__device__ __forceinline__ int seg0_of(const AsmArgs& A, int e) { return A.g.elem_seg0 ? A.g.elem_seg0[e] : e; }
-
-__device__ __forceinline__ RoundExt round_extent(const AsmArgs& A, int e0, int e_end, int lane) {
-    RoundExt x;
-    x.e0 = e0;
-    const int idx = e0 + lane;
-    const bool in = idx <= e_end && lane <= kMaxE;
-    x.off = in ? A.adj_off[idx] : 0;
-    x.goff = in ? A.grp_off[idx] : 0;
-    x.sg = in ? seg0_of(A, idx) : 0;
-    x.k0 = __shfl_sync(kFull, x.off, 0);
-    x.g0 = __shfl_sync(kFull, x.goff, 0);
-    x.sg0 = __shfl_sync(kFull, x.sg, 0);
-    // element i of the round is taken while the items fit one warp and the segments fit the staging buffer
-    const bool ok = in && lane >= 1 && (x.off - x.k0 <= kWarp) && (x.sg - x.sg0 <= kMaxSeg);
-    const unsigned m = __ballot_sync(kFull, ok) >> 1;
-    x.ne = __ffs(~m) - 1;                   // length of the run of set bits (both conditions are monotone)
-    if (x.ne == 0) __trap();                // an element with more than 32 items / kMaxSeg segments: rejected by the host entry
-    x.k1 = __shfl_sync(kFull, x.off, x.ne);
-    x.g1 = __shfl_sync(kFull, x.goff, x.ne);
-    x.nsg = __shfl_sync(kFull, x.sg, x.ne) - x.sg0;
+__device__ __forceinline__ Round load_round(const int* __restrict__ tab, int r, int lane) {
+    const int *w_off = tab, *w_goff = tab + kTab, *w_sg = tab + 2 * kTab, *w_round = tab + 4 * kTab;
+    Round x;
+    x.e0 = w_round[r];
+    x.ne = w_round[r + 1] - x.e0;
+    const int i = x.e0 + (lane <= x.ne ? lane : 0);
+    x.off = w_off[i];
+    x.goff = w_goff[i];
+    x.sg = w_sg[i];
+    x.k0 = w_off[x.e0]; x.k1 = w_off[x.e0 + x.ne];
+    x.g0 = w_goff[x.e0]; x.g1 = w_goff[x.e0 + x.ne];
+    x.sg0 = w_sg[x.e0]; x.nsg = w_sg[x.e0 + x.ne] - x.sg0;
     return x;
 }
 
-struct ItemRegs {
-    int item, nbr;
-    unsigned char upw;
+struct Items {
+    int item, nbr, og;
+    unsigned upw;
 };
 
-// cp.async staging of one round into buffer `sb` (everything an item needs, copied once)
+__device__ __forceinline__ Items load_items(const AsmArgs& A, const int* __restrict__ tab, int r, int lane) {
+    const int *w_off = tab, *w_round = tab + 4 * kTab;
+    const int k0 = w_off[w_round[r]], k1 = w_off[w_round[r + 1]];
+    Items it;
+    it.item = 0; it.nbr = 0; it.og = 0; it.upw = 0;
+    if (lane < k1 - k0) {
+        it.item = A.adj_item[k0 + lane];
+        it.nbr = A.adj_nb[k0 + lane];
+    }
+    return it;
+}
+
+// cp.async staging of one round into buffer `sb` (everything an item needs, copied once); the two warps share the copies
 template <int P, int RS, bool DIFF, bool ADV>
-__device__ __forceinline__ ItemRegs stage_round(const AsmArgs& A, unsigned char* __restrict__ sb, const RoundExt& x, int lane) {
+__device__ __forceinline__ void stage_round(const AsmArgs& A, unsigned char* __restrict__ sb, const Round& x, Items& it, int e_beg,
+                                            int warp, int lane) {
     using DM = Dm<P, RS>;
     using S = FaceSmem<P, RS, DIFF, ADV>;
     constexpr int QE = DM::QE;
-    ItemRegs it;
-    it.item = 0; it.nbr = 0; it.upw = 0;
     const size_t F = (size_t)A.g.n_iface;
     if (lane < x.k1 - x.k0) {
-        it.item = A.adj_item[x.k0 + lane];
-        it.nbr = A.adj_nb[x.k0 + lane];
         const int f = (it.item & 0x7fffffff) >> 1;
         if (A.c.if_upwind) it.upw = A.c.if_upwind[f];
+        it.og = A.g.elem_gid ? A.g.elem_gid[it.nbr] : it.nbr;
         unsigned char* dst = sb + lane * 16;
-        const double2* rec = reinterpret_cast<const double2*>(A.frec + f);
-        const double2* box = reinterpret_cast<const double2*>(A.ebox + it.nbr);
+        if (warp == 0) {
+            const double2* rec = reinterpret_cast<const double2*>(A.frec + f);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            __pipeline_memcpy_async(dst + k * 512, rec + k, 16);
-            __pipeline_memcpy_async(dst + (4 + k) * 512, box + k, 16);
-        }
-#pragma unroll
-        for (int q = 0; q < QE; ++q) {
-            const size_t m = (size_t)q * F + f;
+            for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(dst + k * 512, rec + k, 16);
             if (DIFF) {
-                __pipeline_memcpy_async(dst + (8 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m, 16);
-                __pipeline_memcpy_async(dst + (9 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m + 1, 16);
+#pragma unroll
+                for (int q = 0; q < QE; ++q) {
+                    const size_t m = (size_t)q * F + f;
+                    __pipeline_memcpy_async(dst + (8 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m, 16);
+                    __pipeline_memcpy_async(dst + (9 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m + 1, 16);
+                }
             }
-            if (ADV) __pipeline_memcpy_async(dst + (8 + 2 * QE + q) * 512, reinterpret_cast<const double2*>(A.c.if_b) + m, 16);
+        } else {
+            const double2* box = reinterpret_cast<const double2*>(A.ebox + it.nbr);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(dst + (4 + k) * 512, box + k, 16);
+            if (ADV) {
+#pragma unroll
+                for (int q = 0; q < QE; ++q)
+                    __pipeline_memcpy_async(dst + (8 + 2 * QE + q) * 512, reinterpret_cast<const double2*>(A.c.if_b) + (size_t)q * F + f, 16);
+            }
         }
     }
-    if (lane < x.ne) {
-        const double2* box = reinterpret_cast<const double2*>(A.ebox + x.e0 + lane);
+    if (warp == 0) {
+        if (lane < x.ne) {
+            const double2* box = reinterpret_cast<const double2*>(A.ebox + e_beg + x.e0 + lane);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(sb + S::OOWN + lane * 64 + k * 16, box + k, 16);
-    }
-    {
+            for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(sb + S::OOWN + lane * 64 + k * 16, box + k, 16);
+        }
+    } else {
         const int pieces = x.nsg * (DM::NV / 2);
         const double2* src = reinterpret_cast<const double2*>(A.vdiag + (size_t)x.sg0 * DM::NV);
         for (int w = lane; w < pieces; w += kWarp) __pipeline_memcpy_async(sb + S::OVD + w * 16, src + w, 16);
     }
-    return it;
 }
 
 __device__ __forceinline__ ElemBox lds_box(const unsigned char* p, int stride) {
@@ -481,109 +496,146 @@ __device__ __forceinline__ void face_pass(const AsmArgs& A, const unsigned char*
     }
 }
 
+// exact zeros are rare: one FSETP per value on the high word (+-0 <=> high word is a float zero and the low word is 0;
+// a denormal with a zero high word only sends the caller to the exact count)
+__device__ __forceinline__ bool maybe_zero(double v) { return __int_as_float(__double2hiint(v)) == 0.0f; }
+
+template <int N>
+__device__ __forceinline__ unsigned count_zeros(const double (&v)[N]) {
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) any |= maybe_zero(v[i]);
+    unsigned z = 0;
+    if (any) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) z += (v[i] == 0.0);
+    }
+    return z;
+}
+
+__device__ __forceinline__ unsigned lowmask(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
 // per-lane view of the round
 struct LaneCtx {
-    bool active, headf;
+    bool active;
     int el;          // element of the item inside the round
     int slot;        // block column slot of the off-diagonal block in its row
     int ro, rowlen;  // first double of the element's rows in the row buffer, doubles per scalar row
     int depth;       // 0 = first item of its neighbour group, k = k-th repeat of the same neighbour
+    int elem_ro, elem_rowlen, elem_dslot, elem_ls;   // lane i < ne: layout of element e0+i (D warp)
     double sgn;
     bool down;
 };
 
+// D warp, one row part: per-lane diagonal partial -> ordered per-element sums (volume segments first, then the faces in item
+// order).  Lane kk < NPR owns value pair kk of every element of the round; res[i] = its sum for element i.
 template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void diag_part(const AsmArgs& A, unsigned char* __restrict__ sm, const unsigned char* __restrict__ sb,
-                                          int lane, const RoundExt& x, const LaneCtx& c, const FaceGeo& g, const ElemBox& bxe,
-                                          double* __restrict__ outd, int maxdepth, unsigned& zeros) {
+__device__ __forceinline__ void diag_sums(const AsmArgs& A, unsigned char* __restrict__ sm, const unsigned char* __restrict__ sb,
+                                          int lane, const Round& x, const LaneCtx& c, const FaceGeo& g, const ElemBox& bxe,
+                                          bool wait_store, double2 (&res)[kMaxE]) {
     using DM = Dm<P, RS>;
     using S = FaceSmem<P, RS, DIFF, ADV>;
-    constexpr int D = DM::D, DD = DM::DD, NB = DM::NB, NV = DM::NV;
+    constexpr int D = DM::D, NB = DM::NB, NV = DM::NV;
     constexpr bool LAST = PART == RS - 1;
     constexpr int NPQ = S::NPQ;                                               // face partial pairs
-    constexpr int NPR = RS == 1 ? NV / 2 : NB / 2 + (LAST ? D / 2 : 0);       // pairs reduced per element in this part
-    constexpr int NIT = (kMaxE * NPR + kWarp - 1) / kWarp;
+    constexpr int NPR = RS == 1 ? NV / 2 : NB / 2 + (LAST ? D / 2 : 0);       // pairs summed per element in this part
+    static_assert(NPR <= kWarp, "one lane per value pair");
     double acc[2 * NPQ];
 #pragma unroll
     for (int v = 0; v < 2 * NPQ; ++v) acc[v] = 0.0;
     if (c.active) face_pass<P, RS, PART, DIFF, ADV, false>(A, sb, lane, g, c.sgn, c.down, bxe, bxe, acc);
     double2* part = reinterpret_cast<double2*>(sm + S::OPART);
-    if (RS == 1 || PART == 0) {
-        if (lane == 0) bulk_wait_read();            // the previous round's bulk store has read the row buffer
-    }
+    if (wait_store && lane == 0) bulk_wait_read();      // the previous round's bulk store has read the row buffer
     __syncwarp();
     if (c.active) {
 #pragma unroll
         for (int kk = 0; kk < NPQ; ++kk) part[kk * kPartStride + lane] = make_double2(acc[2 * kk], acc[2 * kk + 1]);
     }
     __syncwarp();
-    const int* s_ls = reinterpret_cast<const int*>(sm + S::OMETA);            // [kMaxE+1] first lane of every element
-    const int* s_ro = s_ls + 16;                                              // [kMaxE]
-    const int* s_rowlen = s_ro + 16;
-    const int* s_dslot = s_rowlen + 16;
-    const int* s_sg = s_dslot + 16;                                           // [kMaxE+1] first staged segment of every element
     const double* vd = reinterpret_cast<const double*>(sb + S::OVD);
-    double2 res[NIT];
-    const int total = x.ne * NPR;
+    const int kk = lane < NPR ? lane : 0;
+    const int vi = pair_dst<P, RS, PART>(kk);
+    const bool faces = 2 * kk < NB;
 #pragma unroll
-    for (int itn = 0; itn < NIT; ++itn) {
-        const int w = lane + itn * kWarp;
-        res[itn] = make_double2(0.0, 0.0);
-        if (w < total) {
-            const int el = w / NPR, kk = w - el * NPR;
-            const int vi = pair_dst<P, RS, PART>(kk);
-            // volume sums first (triangles, main.py:315), then the faces in item order
+    for (int i = 0; i < kMaxE; ++i) {
+        res[i] = make_double2(0.0, 0.0);
+        if (i < x.ne) {                                  // warp-uniform
+            const int s0 = __shfl_sync(kFull, x.sg, i) - x.sg0, s1 = __shfl_sync(kFull, x.sg, i + 1) - x.sg0;
+            const int l0 = __shfl_sync(kFull, c.elem_ls, i), l1 = __shfl_sync(kFull, c.elem_ls, i + 1);
             double2 v = make_double2(0.0, 0.0);
-            for (int s = s_sg[el]; s < s_sg[el + 1]; ++s) {
+            for (int s = s0; s < s1; ++s) {              // triangles first (main.py:315) ...
                 const double2 t = *reinterpret_cast<const double2*>(vd + (size_t)s * NV + vi);
                 v.x += t.x;
                 v.y += t.y;
             }
-            if (2 * kk < NB) {
-                const int l0 = s_ls[el], l1 = s_ls[el + 1];
-                for (int l = l0; l < l1; ++l) {
-                    const double2 t = part[kk * kPartStride + l];
-                    v.x += t.x;
-                    v.y += t.y;
+            if (faces) {
+                for (int l = l0; l < l1; l += 4) {       // ... then the faces in item order; four loads in flight (x + 0.0 = x)
+                    double2 t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) t[u] = l + u < l1 ? part[kk * kPartStride + l + u] : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        v.x += t[u].x;
+                        v.y += t[u].y;
+                    }
                 }
             }
-            res[itn] = v;
+            res[i] = v;
         }
     }
-    __syncwarp();                                   // all partials are read: the row buffer may be written (RS == 1 alias)
+}
+
+template <int P, int RS, int PART, bool DIFF, bool ADV>
+__device__ __forceinline__ void diag_store(const AsmArgs& A, int lane, const Round& x, const LaneCtx& c, int e_first,
+                                           double* __restrict__ outd, const double2 (&res)[kMaxE], bool count, unsigned& zeros) {
+    using DM = Dm<P, RS>;
+    constexpr int D = DM::D, DD = DM::DD, NB = DM::NB, NV = DM::NV;
+    constexpr bool LAST = PART == RS - 1;
+    constexpr int NPR = RS == 1 ? NV / 2 : NB / 2 + (LAST ? D / 2 : 0);
+    const int vi = pair_dst<P, RS, PART>(lane < NPR ? lane : 0);
+    const int r0 = vi / D, c0 = vi - r0 * D, r1 = (vi + 1) / D, c1 = (vi + 1) - r1 * D;
 #pragma unroll
-    for (int itn = 0; itn < NIT; ++itn) {
-        const int w = lane + itn * kWarp;
-        if (w < total) {
-            const int el = w / NPR, kk = w - el * NPR;
-            const int vi = pair_dst<P, RS, PART>(kk);
-            const int e = x.e0 + el;
-            const int ro = s_ro[el], rowlen = s_rowlen[el], ds = s_dslot[el];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int v = vi + h;
-                const double val = h ? res[itn].y : res[itn].x;
-                if (v < DD) {
-                    outd[ro + (v / D) * rowlen + ds * D + (v % D)] = val;
-                    if (maxdepth == 0) zeros += (val == 0.0);
-                } else if (v < NV) {
-                    A.load[(size_t)e * D + (v - DD)] = val;
+    for (int i = 0; i < kMaxE; ++i) {
+        if (i < x.ne) {
+            const int ro = __shfl_sync(kFull, c.elem_ro, i), rowlen = __shfl_sync(kFull, c.elem_rowlen, i);
+            const int ds = __shfl_sync(kFull, c.elem_dslot, i);
+            if (lane < NPR) {
+                const int e = e_first + i;
+                double* base = outd + ro + ds * D;
+                if ((D & 1) == 0 && vi + 1 < DD) {
+                    *reinterpret_cast<double2*>(base + r0 * rowlen + c0) = res[i];
+                    if (count) zeros += (unsigned)(maybe_zero(res[i].x) && res[i].x == 0.0) + (unsigned)(maybe_zero(res[i].y) && res[i].y == 0.0);
+                } else {
+                    if (vi < DD) {
+                        base[r0 * rowlen + c0] = res[i].x;
+                        if (count) zeros += (unsigned)(res[i].x == 0.0);
+                    } else {
+                        A.load[(size_t)e * D + (vi - DD)] = res[i].x;
+                    }
+                    if (vi + 1 < DD) {
+                        base[r1 * rowlen + c1] = res[i].y;
+                        if (count) zeros += (unsigned)(res[i].y == 0.0);
+                    } else if (vi + 1 < NV) {
+                        A.load[(size_t)e * D + (vi + 1 - DD)] = res[i].y;
+                    }
                 }
             }
         }
     }
 }
 
+// O warp, one row part: the off-diagonal block of the lane's item -> its slot in the row buffer
 template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void off_part(const AsmArgs& A, const unsigned char* __restrict__ sb, int lane, const LaneCtx& c,
-                                         const FaceGeo& g, const ElemBox& bxe, const ElemBox& bxo, double* __restrict__ outd,
-                                         int maxdepth, unsigned& zeros) {
+__device__ __forceinline__ void off_block(const AsmArgs& A, const unsigned char* __restrict__ sb, int lane, const LaneCtx& c,
+                                          const FaceGeo& g, const ElemBox& bxe, const ElemBox& bxo, double* __restrict__ outd,
+                                          int maxdepth, bool sync_before_store, unsigned& zeros) {
     using DM = Dm<P, RS>;
     constexpr int D = DM::D, RJ = DM::RJ, NB = DM::NB, J0 = PART * RJ;
     double acc[NB];
 #pragma unroll
     for (int v = 0; v < NB; ++v) acc[v] = 0.0;
     if (c.active) face_pass<P, RS, PART, DIFF, ADV, true>(A, sb, lane, g, c.sgn, c.down, bxe, bxo, acc);
+    if (sync_before_store) cta_sync(2);              // [B] the D warp is done with the partial buffer (= the row buffer)
     double* dst0 = outd + c.ro + c.slot * D;
     if (c.active && c.depth == 0) {
 #pragma unroll
@@ -597,10 +649,7 @@ __device__ __forceinline__ void off_part(const AsmArgs& A, const unsigned char* 
                 for (int i = 0; i < D; ++i) dst[i] = acc[jj * D + i];
             }
         }
-        if (maxdepth == 0) {
-#pragma unroll
-            for (int v = 0; v < NB; ++v) zeros += (acc[v] == 0.0);
-        }
+        if (maxdepth == 0) zeros += count_zeros<NB>(acc);
     }
     // faces that repeat the previous neighbour add to its block, in item order
     for (int dd = 1; dd <= maxdepth; ++dd) {
@@ -617,88 +666,102 @@ __device__ __forceinline__ void off_part(const AsmArgs& A, const unsigned char* 
 }
 
 template <int P, int RS, bool DIFF, bool ADV>
-__global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ AsmArgs A) {
+__global__ void __launch_bounds__(kFaceThreads) dg_face_kernel(const __grid_constant__ AsmArgs A) {
     using DM = Dm<P, RS>;
     using S = FaceSmem<P, RS, DIFF, ADV>;
     constexpr int D = DM::D, DD = DM::DD;
     extern __shared__ __align__(128) unsigned char sm[];
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int e_beg = blockIdx.x * kWindow;
     const int e_end = min(e_beg + kWindow, A.g.n_rows);
+    const int nw = e_end - e_beg;
+    int* tab = reinterpret_cast<int*>(sm + S::OWIN);
+    int *w_off = tab, *w_goff = tab + kTab, *w_sg = tab + 2 * kTab, *w_eg = tab + 3 * kTab, *w_round = tab + 4 * kTab;
+    // ---- window tables + the rounds of the window ---------------------------------------------------------------------------
+    for (int i = tid; i <= nw; i += kFaceThreads) {
+        w_off[i] = A.adj_off[e_beg + i];
+        w_goff[i] = A.grp_off[e_beg + i];
+        w_sg[i] = A.g.elem_seg0 ? A.g.elem_seg0[e_beg + i] : e_beg + i;
+        if (i < nw) w_eg[i] = gid_of(A, e_beg + i);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int e = 0, nr = 0;
+        while (e < nw) {
+            if (lane == 0) w_round[nr] = e;
+            const int idx = e + lane;
+            const bool in = idx <= nw && lane <= kMaxE;
+            const int off = in ? w_off[idx] : 0, sg = in ? w_sg[idx] : 0;
+            const int k0 = __shfl_sync(kFull, off, 0), sg0 = __shfl_sync(kFull, sg, 0);
+            // an element is taken while the items fit one warp and the segments fit the staging buffer
+            const bool ok = in && lane >= 1 && (off - k0 <= kWarp) && (sg - sg0 <= kMaxSeg);
+            const unsigned m = __ballot_sync(kFull, ok) >> 1;
+            const int ne = __ffs(~m) - 1;          // length of the run of set bits (both conditions are monotone)
+            if (ne == 0) __trap();                 // more than 32 items / kMaxSeg segments in one element: rejected by the host entry
+            e += ne;
+            ++nr;
+        }
+        if (lane == 0) {
+            w_round[nr] = nw;
+            w_round[kTab - 1] = nr;
+        }
+    }
+    __syncthreads();
+    const int nr = w_round[kTab - 1];
     unsigned zeros = 0;
-    int* s_ls = reinterpret_cast<int*>(sm + S::OMETA);
-    int* s_ro = s_ls + 16;
-    int* s_rowlen = s_ro + 16;
-    int* s_dslot = s_rowlen + 16;
-    int* s_sg = s_dslot + 16;
 
-    RoundExt x = round_extent(A, e_beg, e_end, lane);
-    ItemRegs it = stage_round<P, RS, DIFF, ADV>(A, sm, x, lane);
+    Items it0 = load_items(A, tab, 0, lane), it1 = it0;
+    if (nr > 1) it1 = load_items(A, tab, 1, lane);
+    {
+        const Round x0 = load_round(tab, 0, lane);
+        stage_round<P, RS, DIFF, ADV>(A, sm, x0, it0, e_beg, warp, lane);
+    }
     __pipeline_commit();
     int buf = 0;
-    while (true) {
-        const int e_next = x.e0 + x.ne;
-        const bool has_next = e_next < e_end;
-        RoundExt xn = x;
-        ItemRegs itn = it;
-        if (has_next) {
-            xn = round_extent(A, e_next, e_end, lane);
-            itn = stage_round<P, RS, DIFF, ADV>(A, sm + (buf ^ 1) * S::STAGE, xn, lane);
+    for (int r = 0; r < nr; ++r) {
+        Items it2 = it1;
+        if (r + 2 < nr) it2 = load_items(A, tab, r + 2, lane);
+        if (r + 1 < nr) {
+            const Round xn = load_round(tab, r + 1, lane);
+            stage_round<P, RS, DIFF, ADV>(A, sm + (buf ^ 1) * S::STAGE, xn, it1, e_beg, warp, lane);
         }
         __pipeline_commit();
         __pipeline_wait_prior(1);
-        __syncwarp();
+        cta_sync(1);                                // [A] the round's staging (copies of both warps) is visible
         const unsigned char* sb = sm + buf * S::STAGE;
+        const Round x = load_round(tab, r, lane);
 
-        // ---- decode the round ------------------------------------------------------------------------------------------
+        // ---- decode the round (both warps) ---------------------------------------------------------------------------------------
         LaneCtx c;
         const int nit = x.k1 - x.k0;
         c.active = lane < nit;
-        const int k = x.k0 + lane;
+        c.elem_ls = x.off - x.k0;                  // lane i <= ne: first lane of element i
         c.el = 0;
 #pragma unroll
         for (int i = 1; i < kMaxE; ++i) {
-            const int o = __shfl_sync(kFull, x.off, i);
-            if (i < x.ne && k >= o) ++c.el;
+            const int o = __shfl_sync(kFull, c.elem_ls, i);
+            if (i < x.ne && lane >= o) ++c.el;
         }
         if (!c.active) c.el = 0;
-        const int e = x.e0 + c.el;
-        const int eg = gid_of(A, e);
-        const int og = c.active ? gid_of(A, it.nbr) : 0;
-        c.headf = c.active && it.item >= 0;
-        int gi = 0, my_dslot = 0;
-        unsigned my_heads = 0;
-        for (int i = 0; i < x.ne; ++i) {
-            const bool mine = c.active && c.el == i;
-            const unsigned hm = __ballot_sync(kFull, mine && c.headf);
-            const unsigned lm = __ballot_sync(kFull, mine && c.headf && og < eg);
-            if (mine) {
-                my_heads = hm & (lanemask_lt() | (1u << lane));
-                gi = __popc(my_heads) - 1;
-            }
-            if (lane == i) my_dslot = __popc(lm);
-        }
-        c.slot = gi + (og > eg ? 1 : 0);
-        c.depth = c.active ? lane - (31 - __clz(my_heads)) : 0;
+        const int my_ls = __shfl_sync(kFull, c.elem_ls, c.el);
+        const int eg = w_eg[x.e0 + c.el];
+        const bool headf = c.active && it0.item >= 0;
+        const unsigned hm = __ballot_sync(kFull, headf);
+        const unsigned below = (2u << lane) - 1u;
+        c.slot = __popc(hm & below & ~lowmask(my_ls)) - 1 + (it0.og > eg ? 1 : 0);
+        c.depth = c.active ? lane - (31 - __clz(hm & below)) : 0;
         const int maxdepth = A.has_dups ? __reduce_max_sync(kFull, c.depth) : 0;
-        // lane i <= ne: layout of element e0+i in the row buffer
+        const unsigned lm = __ballot_sync(kFull, headf && it0.og < eg);
+        const int ls_next = __shfl_down_sync(kFull, c.elem_ls, 1);
         const int goff_next = __shfl_down_sync(kFull, x.goff, 1);
-        const int my_ro = DD * ((x.goff - x.g0) + lane);
-        const int my_rowlen = (goff_next - x.goff + 1) * D;
-        if (lane <= x.ne) {
-            s_ls[lane] = x.off - x.k0;
-            s_sg[lane] = x.sg - x.sg0;
-        }
-        if (lane < x.ne) {
-            s_ro[lane] = my_ro;
-            s_rowlen[lane] = my_rowlen;
-            s_dslot[lane] = my_dslot;
-        }
-        c.ro = __shfl_sync(kFull, my_ro, c.el);
-        c.rowlen = __shfl_sync(kFull, my_rowlen, c.el);
-        const int side = it.item & 1;
+        c.elem_dslot = __popc(lm & lowmask(ls_next) & ~lowmask(c.elem_ls));
+        c.elem_ro = DD * ((x.goff - x.g0) + lane);
+        c.elem_rowlen = (goff_next - x.goff + 1) * D;
+        c.ro = __shfl_sync(kFull, c.elem_ro, c.el);
+        c.rowlen = __shfl_sync(kFull, c.elem_rowlen, c.el);
+        const int side = it0.item & 1;
         c.sgn = side ? -1.0 : 1.0;
-        c.down = A.c.if_upwind ? ((it.upw != 0) == (side == 1)) : false;
+        c.down = A.c.if_upwind ? ((it0.upw != 0) == (side == 1)) : false;
         FaceGeo g;
         {
             const unsigned char* p = sb + lane * 16;
@@ -707,40 +770,47 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
             g.midx = a.x; g.midy = a.y; g.tanx = b.x; g.tany = b.y; g.nx = cc.x; g.ny = cc.y; g.De = d.x; g.sigma = d.y;
         }
         const ElemBox bxe = lds_box(sb + S::OOWN + c.el * 64, 16);
-        const ElemBox bxo = lds_box(sb + 4 * 512 + lane * 16, 512);
         // first byte of the round's rows in the value array; the row buffer starts at the same 16-byte phase
-        double* gdst = A.data + (size_t)DD * ((size_t)x.g0 + x.e0);
+        double* gdst = A.data + (size_t)DD * ((size_t)x.g0 + e_beg + x.e0);
         const int oshift = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
         double* outd = reinterpret_cast<double*>(sm + S::OOUT + oshift);
-
-        // ---- diagonal contributions: per-lane partial -> ordered per-element sum -> diagonal block, load --------------------
-        diag_part<P, RS, 0, DIFF, ADV>(A, sm, sb, lane, x, c, g, bxe, outd, maxdepth, zeros);
-        if (RS > 1) diag_part<P, RS, RS - 1, DIFF, ADV>(A, sm, sb, lane, x, c, g, bxe, outd, maxdepth, zeros);
-        // ---- off-diagonal blocks ------------------------------------------------------------------------------------------
-        off_part<P, RS, 0, DIFF, ADV>(A, sb, lane, c, g, bxe, bxo, outd, maxdepth, zeros);
-        if (RS > 1) off_part<P, RS, RS - 1, DIFF, ADV>(A, sb, lane, c, g, bxe, bxo, outd, maxdepth, zeros);
-        __syncwarp();
         const int ndbl = DD * ((x.g1 - x.g0) + x.ne);      // doubles of the round's rows
+
+        if (warp == 0) {
+            // ---- D warp: diagonal contributions -> ordered sums -> diagonal blocks, load -----------------------------------------
+            double2 res[kMaxE];
+            diag_sums<P, RS, 0, DIFF, ADV>(A, sm, sb, lane, x, c, g, bxe, true, res);
+            cta_sync(2);                            // [B] all partials are read, the previous bulk store is done: rows may be written
+            diag_store<P, RS, 0, DIFF, ADV>(A, lane, x, c, e_beg + x.e0, outd, res, maxdepth == 0, zeros);
+            if (RS > 1) {
+                diag_sums<P, RS, RS - 1, DIFF, ADV>(A, sm, sb, lane, x, c, g, bxe, false, res);
+                diag_store<P, RS, RS - 1, DIFF, ADV>(A, lane, x, c, e_beg + x.e0, outd, res, maxdepth == 0, zeros);
+            }
+        } else {
+            // ---- O warp: off-diagonal blocks ---------------------------------------------------------------------------------------
+            const ElemBox bxo = lds_box(sb + 4 * 512 + lane * 16, 512);
+            off_block<P, RS, 0, DIFF, ADV>(A, sb, lane, c, g, bxe, bxo, outd, maxdepth, true, zeros);
+            if (RS > 1) off_block<P, RS, RS - 1, DIFF, ADV>(A, sb, lane, c, g, bxe, bxo, outd, maxdepth, false, zeros);
+        }
+        fence_async_smem();
+        cta_sync(3);                                // [C] the rows of the round are complete
         if (maxdepth > 0) {
             // merged blocks: count the exact zeros of the finished rows (the per-lane counts above were skipped)
-            for (int w = lane; w < ndbl; w += kWarp) zeros += (outd[w] == 0.0);
+            for (int w = tid; w < ndbl; w += kFaceThreads) zeros += (outd[w] == 0.0);
         }
-        // ---- one bulk store for all rows of the round ---------------------------------------------------------------------------
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
+        // ---- one bulk store for all rows of the round ------------------------------------------------------------------------------
+        if (tid == 0) {
             int lo = 0, n = ndbl;
             if (oshift) { gdst[0] = outd[0]; lo = 1; --n; }
             const int core = n & ~1;
             if (core) bulk_s2g(gdst + lo, outd + lo, (uint32_t)core * 8);
             if (n & 1) gdst[lo + core] = outd[lo + core];
         }
-        if (!has_next) break;
-        x = xn;
-        it = itn;
+        it0 = it1;
+        it1 = it2;
         buf ^= 1;
     }
-    if (lane == 0) bulk_wait_read();
+    if (tid == 0) bulk_wait_read();
     if (zeros) atomicAdd(A.zero_count, (unsigned long long)zeros);
 }
 
@@ -758,7 +828,7 @@ static int launch(const AsmArgs& A, cudaStream_t st) {
         RB_LAUNCH_CHECK("dg_volume_kernel");
     }
     const int blocks = (int)div_up(A.g.n_rows, kWindow);
-    fk<<<blocks, kWarp, FS::TOTAL, st>>>(A);
+    fk<<<blocks, kFaceThreads, FS::TOTAL, st>>>(A);
     RB_LAUNCH_CHECK("dg_face_kernel");
     return 0;
 }

@@ -28,7 +28,6 @@ namespace rb {
 namespace items {
 
 constexpr int kWarp = 32;
-constexpr int kMaxE = 8;        // elements per face round (bounds the shared-memory row buffer)
 constexpr int kMaxSeg = 8;      // volume segments staged per face round
 constexpr int kWindow = 64;     // consecutive elements per face CTA
 constexpr unsigned kFull = 0xffffffffu;
@@ -69,9 +68,6 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t 
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// CTA-wide barrier of the face kernel (64 threads); the two warps reach it from different code paths
-__device__ __forceinline__ void cta_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
@@ -303,26 +299,34 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
 // =======================================================================================================================
 // face kernel
 // =======================================================================================================================
-constexpr int kFaceThreads = 64;   // warp 0 ("D"): diagonal contributions + their ordered sums; warp 1 ("O"): off-diagonal blocks
+// One warp per CTA, one lane per (element, face) item, ONE sweep over the face points of a round:
+//   item lanes    evaluate the element's basis once per point: P, Q (rows) and U, V (columns of the diagonal part) go to a
+//                 shared-memory record; the neighbour's basis gives the columns of the off-diagonal block, which the lane
+//                 accumulates in registers;
+//   row owners    lane (i, j) owns row j of the diagonal block of element i of the round: it starts from the volume sums and
+//                 adds, item by item in adjacency order, P_j U + Q_j V from the records -- no cross-lane reduction, no
+//                 partial blocks, a fixed order that does not depend on the partition.
+// Latency is hidden by occupancy (single staging buffer, like the volume kernel); only the item indices are fetched one
+// round ahead so that the dependent chain adjacency -> item -> face data never stalls a round.
 constexpr int kTab = 72;           // ints per window table (kWindow + 1 entries used)
 
 template <int P, int RS, bool DIFF, bool ADV>
 struct FaceSmem {
     using DM = Dm<P, RS>;
+    static constexpr int NT = P <= 2 ? 1 : 2;                                   // row-owner tasks per lane
+    static constexpr int MAXE = (kWarp * NT) / DM::D < 8 ? (kWarp * NT) / DM::D : 8;   // elements per round
     static constexpr int NPL = 8 + 3 * DM::QE;                  // 16-byte planes per item: record 4, neighbour box 4, a 2/point, b 1/point
     static constexpr int PLANES = NPL * 512;
-    static constexpr int OOWN = PLANES;                          // own boxes of the round's elements [kMaxE][64 bytes]
-    static constexpr int OVD = OOWN + kMaxE * 64;                // volume sums of the round's segments [kMaxSeg][NV]
-    static constexpr int STAGE = OVD + kMaxSeg * DM::NV * 8;     // one staging buffer
-    static constexpr int OOUT = 2 * STAGE;                       // block rows of the round (+ 16 bytes of alignment shift)
-    static constexpr int OUTB = (32 + kMaxE) * DM::DD * 8 + 16;
-    static constexpr int NPQ = (DM::NB + 1) / 2;                 // pairs of one diagonal partial
-    static constexpr int PARTB = NPQ * kPartStride * 16;
-    // one pass: the diagonal partials use the (still empty) row buffer; several passes: a buffer of their own
-    static constexpr int OPART = RS == 1 ? OOUT : OOUT + OUTB;
-    static constexpr int OWIN = RS == 1 ? (OOUT + (OUTB > PARTB ? OUTB : PARTB)) : (OPART + PARTB);
+    static constexpr int OOWN = PLANES;                          // own boxes of the round's elements [MAXE][64 bytes]
+    static constexpr int OVD = OOWN + MAXE * 64;                 // volume sums of the round's segments [kMaxSeg][NV]
+    static constexpr int STAGE = OVD + kMaxSeg * DM::NV * 8;     // the staging buffer
+    static constexpr int OOUT = STAGE;                           // block rows of the round (+ 16 bytes of alignment shift)
+    static constexpr int OUTB = (32 + MAXE) * DM::DD * 8 + 16;
+    static constexpr int REC = 4 * DM::D * 8 + 16;               // P, Q, U, V of one item at one point (+16: conflict-free lane stride)
+    static constexpr int PQUVB = 32 * REC;                       // lives in the row buffer until the rows are written
+    static constexpr int OWIN = OOUT + (OUTB > PQUVB ? OUTB : PQUVB);
     static constexpr int TOTAL = OWIN + 5 * kTab * 4;            // window tables: adj_off, grp_off, first segment, gid, rounds
-    static_assert(STAGE % 16 == 0 && OUTB % 16 == 0 && PARTB % 16 == 0, "alignment");
+    static_assert(STAGE % 16 == 0 && OUTB % 16 == 0 && REC % 16 == 0, "alignment");
 };
 
 struct FaceGeo {
@@ -352,15 +356,14 @@ __device__ __forceinline__ Round load_round(const int* __restrict__ tab, int r, 
 }
 
 struct Items {
-    int item, nbr, og;
-    unsigned upw;
+    int item, nbr;
 };
 
 __device__ __forceinline__ Items load_items(const AsmArgs& A, const int* __restrict__ tab, int r, int lane) {
     const int *w_off = tab, *w_round = tab + 4 * kTab;
     const int k0 = w_off[w_round[r]], k1 = w_off[w_round[r + 1]];
     Items it;
-    it.item = 0; it.nbr = 0; it.og = 0; it.upw = 0;
+    it.item = 0; it.nbr = 0;
     if (lane < k1 - k0) {
         it.item = A.adj_item[k0 + lane];
         it.nbr = A.adj_nb[k0 + lane];
@@ -368,49 +371,40 @@ __device__ __forceinline__ Items load_items(const AsmArgs& A, const int* __restr
     return it;
 }
 
-// cp.async staging of one round into buffer `sb` (everything an item needs, copied once); the two warps share the copies
+// cp.async staging of one round (everything an item needs, copied once)
 template <int P, int RS, bool DIFF, bool ADV>
-__device__ __forceinline__ void stage_round(const AsmArgs& A, unsigned char* __restrict__ sb, const Round& x, Items& it, int e_beg,
-                                            int warp, int lane) {
+__device__ __forceinline__ void stage_round(const AsmArgs& A, unsigned char* __restrict__ sb, const Round& x, const Items& it,
+                                            int e_beg, int lane) {
     using DM = Dm<P, RS>;
     using S = FaceSmem<P, RS, DIFF, ADV>;
     constexpr int QE = DM::QE;
     const size_t F = (size_t)A.g.n_iface;
     if (lane < x.k1 - x.k0) {
         const int f = (it.item & 0x7fffffff) >> 1;
-        if (A.c.if_upwind) it.upw = A.c.if_upwind[f];
-        it.og = A.g.elem_gid ? A.g.elem_gid[it.nbr] : it.nbr;
         unsigned char* dst = sb + lane * 16;
-        if (warp == 0) {
-            const double2* rec = reinterpret_cast<const double2*>(A.frec + f);
+        const double2* rec = reinterpret_cast<const double2*>(A.frec + f);
+        const double2* box = reinterpret_cast<const double2*>(A.ebox + it.nbr);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(dst + k * 512, rec + k, 16);
+        for (int k = 0; k < 4; ++k) {
+            __pipeline_memcpy_async(dst + k * 512, rec + k, 16);
+            __pipeline_memcpy_async(dst + (4 + k) * 512, box + k, 16);
+        }
+#pragma unroll
+        for (int q = 0; q < QE; ++q) {
+            const size_t m = (size_t)q * F + f;
             if (DIFF) {
-#pragma unroll
-                for (int q = 0; q < QE; ++q) {
-                    const size_t m = (size_t)q * F + f;
-                    __pipeline_memcpy_async(dst + (8 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m, 16);
-                    __pipeline_memcpy_async(dst + (9 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m + 1, 16);
-                }
+                __pipeline_memcpy_async(dst + (8 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m, 16);
+                __pipeline_memcpy_async(dst + (9 + 2 * q) * 512, reinterpret_cast<const double2*>(A.c.if_a) + 2 * m + 1, 16);
             }
-        } else {
-            const double2* box = reinterpret_cast<const double2*>(A.ebox + it.nbr);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(dst + (4 + k) * 512, box + k, 16);
-            if (ADV) {
-#pragma unroll
-                for (int q = 0; q < QE; ++q)
-                    __pipeline_memcpy_async(dst + (8 + 2 * QE + q) * 512, reinterpret_cast<const double2*>(A.c.if_b) + (size_t)q * F + f, 16);
-            }
+            if (ADV) __pipeline_memcpy_async(dst + (8 + 2 * QE + q) * 512, reinterpret_cast<const double2*>(A.c.if_b) + m, 16);
         }
     }
-    if (warp == 0) {
-        if (lane < x.ne) {
-            const double2* box = reinterpret_cast<const double2*>(A.ebox + e_beg + x.e0 + lane);
+    if (lane < x.ne) {
+        const double2* box = reinterpret_cast<const double2*>(A.ebox + e_beg + x.e0 + lane);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(sb + S::OOWN + lane * 64 + k * 16, box + k, 16);
-        }
-    } else {
+        for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(sb + S::OOWN + lane * 64 + k * 16, box + k, 16);
+    }
+    {
         const int pieces = x.nsg * (DM::NV / 2);
         const double2* src = reinterpret_cast<const double2*>(A.vdiag + (size_t)x.sg0 * DM::NV);
         for (int w = lane; w < pieces; w += kWarp) __pipeline_memcpy_async(sb + S::OVD + w * 16, src + w, 16);
@@ -423,77 +417,6 @@ __device__ __forceinline__ ElemBox lds_box(const unsigned char* p, int stride) {
     ElemBox b;
     b.mx = m.x; b.my = m.y; b.ihx = ih.x; b.ihy = ih.y; b.s05x = s05.x; b.s05y = s05.y; b.s15x = s15.x; b.s15y = s15.y;
     return b;
-}
-
-// One pass over the face points of the lane's item: rows [J0, J0+RJ) of the diagonal (OFF = false: columns = basis of the
-// element) or off-diagonal block (OFF = true: columns = basis of the neighbour).
-//   P_r = s phi_r, Q_r = -F_r/2, V_c = W s phi_c, U_c = (sigma + gamma) V_c - W F_c/2;  B[r,c] += P_r U_c + Q_r V_c
-// (full_assembly.py:174-212; s = +1 on the K1 side, -1 on the K2 side).
-template <int P, int RS, int PART, bool DIFF, bool ADV, bool OFF>
-__device__ __forceinline__ void face_pass(const AsmArgs& A, const unsigned char* __restrict__ sb, int lane, const FaceGeo& g,
-                                          double sgn, bool down, const ElemBox& bxe, const ElemBox& bxo,
-                                          double* __restrict__ acc) {
-    using DM = Dm<P, RS>;
-    constexpr int D = DM::D, RJ = DM::RJ, QE = DM::QE, J0 = PART * RJ;
-#pragma unroll 1
-    for (int q = 0; q < QE; ++q) {
-        double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
-        if (DIFF) {
-            const double2 r0 = *reinterpret_cast<const double2*>(sb + (8 + 2 * q) * 512 + lane * 16);
-            const double2 r1 = *reinterpret_cast<const double2*>(sb + (9 + 2 * q) * 512 + lane * 16);
-            a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
-        }
-        if (ADV) {
-            const double2 bb = *reinterpret_cast<const double2*>(sb + (8 + 2 * QE + q) * 512 + lane * 16);
-            b0 = bb.x; b1 = bb.y;
-        }
-        const double x = g.midx + A.xe[q] * g.tanx;
-        const double y = g.midy + A.xe[q] * g.tany;
-        const double W = g.De * A.we[q];
-        double atn0 = 0, atn1 = 0, gamma = 0;
-        if (DIFF) {
-            // F_k = n . (a grad phi_k) = (a^T n) . grad phi_k
-            atn0 = g.nx * a00 + g.ny * a10;
-            atn1 = g.nx * a01 + g.ny * a11;
-        }
-        if (ADV) {
-            const double beta = b0 * g.nx + b1 * g.ny;
-            gamma = down ? -sgn * beta : 0.0;
-        }
-        const double hw0 = -0.5 * W * atn0, hw1 = -0.5 * W * atn1;     // -W/2 * a^T n
-        const double sg = g.sigma + gamma;
-        double phi[D], gx[D], gy[D];
-        eval_basis<P, DIFF>(x, y, bxe, A.lc, phi, gx, gy);
-        double Pr[RJ], Qr[RJ];
-#pragma unroll
-        for (int jj = 0; jj < RJ; ++jj) {
-            const int j = J0 + jj;
-            Pr[jj] = sgn * phi[j];
-            Qr[jj] = 0.0;
-            if (DIFF) {
-                if (gx_nz<P>(j) && gy_nz<P>(j)) Qr[jj] = -0.5 * (atn0 * gx[j] + atn1 * gy[j]);
-                else if (gx_nz<P>(j)) Qr[jj] = -0.5 * (atn0 * gx[j]);
-                else if (gy_nz<P>(j)) Qr[jj] = -0.5 * (atn1 * gy[j]);
-            }
-        }
-        const double Ws = OFF ? -(W * sgn) : W * sgn;
-        if (OFF) eval_basis<P, DIFF>(x, y, bxo, A.lc, phi, gx, gy);
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            const double Vc = Ws * phi[i];
-            double Uc = sg * Vc;
-            if (DIFF && gy_nz<P>(i)) Uc = fma(hw1, gy[i], Uc);
-            if (DIFF && gx_nz<P>(i)) Uc = fma(hw0, gx[i], Uc);
-#pragma unroll
-            for (int jj = 0; jj < RJ; ++jj) {
-                const int j = J0 + jj;
-                double v = acc[jj * D + i];
-                v = fma(Pr[jj], Uc, v);
-                if (DIFF && (gx_nz<P>(j) || gy_nz<P>(j))) v = fma(Qr[jj], Vc, v);
-                acc[jj * D + i] = v;
-            }
-        }
-    }
 }
 
 // exact zeros are rare: one FSETP per value on the high word (+-0 <=> high word is a float zero and the low word is 0;
@@ -522,246 +445,255 @@ struct LaneCtx {
     int slot;        // block column slot of the off-diagonal block in its row
     int ro, rowlen;  // first double of the element's rows in the row buffer, doubles per scalar row
     int depth;       // 0 = first item of its neighbour group, k = k-th repeat of the same neighbour
-    int elem_ro, elem_rowlen, elem_dslot, elem_ls;   // lane i < ne: layout of element e0+i (D warp)
     double sgn;
     bool down;
 };
 
-// D warp, one row part: per-lane diagonal partial -> ordered per-element sums (volume segments first, then the faces in item
-// order).  Lane kk < NPR owns value pair kk of every element of the round; res[i] = its sum for element i.
-template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void diag_sums(const AsmArgs& A, unsigned char* __restrict__ sm, const unsigned char* __restrict__ sb,
-                                          int lane, const Round& x, const LaneCtx& c, const FaceGeo& g, const ElemBox& bxe,
-                                          bool wait_store, double2 (&res)[kMaxE]) {
+// row-owner task: row `row` of the diagonal block of element `el` of the round, fed by the items of lanes [l0, l1)
+struct RowTask {
+    bool on;
+    int el, row, l0, l1, ro, rowlen, dslot;
+};
+
+// One sweep over the face points for row part PART of the off-diagonal blocks (and, in part 0, all diagonal rows):
+//   P_r = s phi_r, Q_r = -F_r/2, V_c = W s phi_c, U_c = (sigma + gamma) V_c - W F_c/2;  B[r,c] += P_r U_c + Q_r V_c
+// (full_assembly.py:174-212; s = +1 on the K1 side, -1 on the K2 side; diagonal part: columns from the element's own basis,
+// off-diagonal part: columns from the neighbour's basis with the opposite sign).
+template <int P, int RS, int PART, bool DIFF, bool ADV, int NT>
+__device__ __forceinline__ void face_sweep(const AsmArgs& A, const unsigned char* __restrict__ sb, unsigned char* __restrict__ pquv,
+                                           int lane, const LaneCtx& c, const FaceGeo& g, const ElemBox& bxe, const ElemBox& bxo,
+                                           const RowTask (&task)[NT], double* __restrict__ oacc,
+                                           double (&racc)[NT][Dm<P, RS>::D]) {
     using DM = Dm<P, RS>;
     using S = FaceSmem<P, RS, DIFF, ADV>;
-    constexpr int D = DM::D, NB = DM::NB, NV = DM::NV;
-    constexpr bool LAST = PART == RS - 1;
-    constexpr int NPQ = S::NPQ;                                               // face partial pairs
-    constexpr int NPR = RS == 1 ? NV / 2 : NB / 2 + (LAST ? D / 2 : 0);       // pairs summed per element in this part
-    static_assert(NPR <= kWarp, "one lane per value pair");
-    double acc[2 * NPQ];
-#pragma unroll
-    for (int v = 0; v < 2 * NPQ; ++v) acc[v] = 0.0;
-    if (c.active) face_pass<P, RS, PART, DIFF, ADV, false>(A, sb, lane, g, c.sgn, c.down, bxe, bxe, acc);
-    double2* part = reinterpret_cast<double2*>(sm + S::OPART);
-    if (wait_store && lane == 0) bulk_wait_read();      // the previous round's bulk store has read the row buffer
-    __syncwarp();
-    if (c.active) {
-#pragma unroll
-        for (int kk = 0; kk < NPQ; ++kk) part[kk * kPartStride + lane] = make_double2(acc[2 * kk], acc[2 * kk + 1]);
-    }
-    __syncwarp();
-    const double* vd = reinterpret_cast<const double*>(sb + S::OVD);
-    const int kk = lane < NPR ? lane : 0;
-    const int vi = pair_dst<P, RS, PART>(kk);
-    const bool faces = 2 * kk < NB;
-#pragma unroll
-    for (int i = 0; i < kMaxE; ++i) {
-        res[i] = make_double2(0.0, 0.0);
-        if (i < x.ne) {                                  // warp-uniform
-            const int s0 = __shfl_sync(kFull, x.sg, i) - x.sg0, s1 = __shfl_sync(kFull, x.sg, i + 1) - x.sg0;
-            const int l0 = __shfl_sync(kFull, c.elem_ls, i), l1 = __shfl_sync(kFull, c.elem_ls, i + 1);
-            double2 v = make_double2(0.0, 0.0);
-            for (int s = s0; s < s1; ++s) {              // triangles first (main.py:315) ...
-                const double2 t = *reinterpret_cast<const double2*>(vd + (size_t)s * NV + vi);
-                v.x += t.x;
-                v.y += t.y;
+    constexpr int D = DM::D, RJ = DM::RJ, QE = DM::QE, J0 = PART * RJ;
+#pragma unroll 1
+    for (int q = 0; q < QE; ++q) {
+        if (c.active) {
+            double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
+            if (DIFF) {
+                const double2 r0 = *reinterpret_cast<const double2*>(sb + (8 + 2 * q) * 512 + lane * 16);
+                const double2 r1 = *reinterpret_cast<const double2*>(sb + (9 + 2 * q) * 512 + lane * 16);
+                a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
             }
-            if (faces) {
-                for (int l = l0; l < l1; l += 4) {       // ... then the faces in item order; four loads in flight (x + 0.0 = x)
-                    double2 t[4];
+            if (ADV) {
+                const double2 bb = *reinterpret_cast<const double2*>(sb + (8 + 2 * QE + q) * 512 + lane * 16);
+                b0 = bb.x; b1 = bb.y;
+            }
+            const double x = g.midx + A.xe[q] * g.tanx;
+            const double y = g.midy + A.xe[q] * g.tany;
+            const double W = g.De * A.we[q];
+            double atn0 = 0, atn1 = 0, gamma = 0;
+            if (DIFF) {
+                // F_k = n . (a grad phi_k) = (a^T n) . grad phi_k
+                atn0 = g.nx * a00 + g.ny * a10;
+                atn1 = g.nx * a01 + g.ny * a11;
+            }
+            if (ADV) {
+                const double beta = b0 * g.nx + b1 * g.ny;
+                gamma = c.down ? -c.sgn * beta : 0.0;
+            }
+            const double hw0 = -0.5 * W * atn0, hw1 = -0.5 * W * atn1;     // -W/2 * a^T n
+            const double sg = g.sigma + gamma;
+            const double Ws = W * c.sgn;
+            double phi[D], gx[D], gy[D];
+            eval_basis<P, DIFF>(x, y, bxe, A.lc, phi, gx, gy);
+            double Pr[D], Qr[D];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) t[u] = l + u < l1 ? part[kk * kPartStride + l + u] : make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        v.x += t[u].x;
-                        v.y += t[u].y;
-                    }
+            for (int j = 0; j < D; ++j) {
+                Pr[j] = c.sgn * phi[j];
+                Qr[j] = 0.0;
+                if (DIFF) {
+                    if (gx_nz<P>(j) && gy_nz<P>(j)) Qr[j] = -0.5 * (atn0 * gx[j] + atn1 * gy[j]);
+                    else if (gx_nz<P>(j)) Qr[j] = -0.5 * (atn0 * gx[j]);
+                    else if (gy_nz<P>(j)) Qr[j] = -0.5 * (atn1 * gy[j]);
                 }
             }
-            res[i] = v;
-        }
-    }
-}
-
-template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void diag_store(const AsmArgs& A, int lane, const Round& x, const LaneCtx& c, int e_first,
-                                           double* __restrict__ outd, const double2 (&res)[kMaxE], bool count, unsigned& zeros) {
-    using DM = Dm<P, RS>;
-    constexpr int D = DM::D, DD = DM::DD, NB = DM::NB, NV = DM::NV;
-    constexpr bool LAST = PART == RS - 1;
-    constexpr int NPR = RS == 1 ? NV / 2 : NB / 2 + (LAST ? D / 2 : 0);
-    const int vi = pair_dst<P, RS, PART>(lane < NPR ? lane : 0);
-    const int r0 = vi / D, c0 = vi - r0 * D, r1 = (vi + 1) / D, c1 = (vi + 1) - r1 * D;
+            if (PART == 0) {
+                // the item's record for the row owners: P, Q, then U, V of the diagonal part
+                double* rec = reinterpret_cast<double*>(pquv + lane * S::REC);
+                double Ue[D], Ve[D];
 #pragma unroll
-    for (int i = 0; i < kMaxE; ++i) {
-        if (i < x.ne) {
-            const int ro = __shfl_sync(kFull, c.elem_ro, i), rowlen = __shfl_sync(kFull, c.elem_rowlen, i);
-            const int ds = __shfl_sync(kFull, c.elem_dslot, i);
-            if (lane < NPR) {
-                const int e = e_first + i;
-                double* base = outd + ro + ds * D;
-                if ((D & 1) == 0 && vi + 1 < DD) {
-                    *reinterpret_cast<double2*>(base + r0 * rowlen + c0) = res[i];
-                    if (count) zeros += (unsigned)(maybe_zero(res[i].x) && res[i].x == 0.0) + (unsigned)(maybe_zero(res[i].y) && res[i].y == 0.0);
+                for (int i = 0; i < D; ++i) {
+                    Ve[i] = Ws * phi[i];
+                    Ue[i] = sg * Ve[i];
+                    if (DIFF && gy_nz<P>(i)) Ue[i] = fma(hw1, gy[i], Ue[i]);
+                    if (DIFF && gx_nz<P>(i)) Ue[i] = fma(hw0, gx[i], Ue[i]);
+                }
+                if ((D & 1) == 0) {
+#pragma unroll
+                    for (int i = 0; i < D; i += 2) {
+                        reinterpret_cast<double2*>(rec)[i >> 1] = make_double2(Pr[i], Pr[i + 1]);
+                        reinterpret_cast<double2*>(rec + D)[i >> 1] = make_double2(Qr[i], Qr[i + 1]);
+                        reinterpret_cast<double2*>(rec + 2 * D)[i >> 1] = make_double2(Ue[i], Ue[i + 1]);
+                        reinterpret_cast<double2*>(rec + 3 * D)[i >> 1] = make_double2(Ve[i], Ve[i + 1]);
+                    }
                 } else {
-                    if (vi < DD) {
-                        base[r0 * rowlen + c0] = res[i].x;
-                        if (count) zeros += (unsigned)(res[i].x == 0.0);
-                    } else {
-                        A.load[(size_t)e * D + (vi - DD)] = res[i].x;
-                    }
-                    if (vi + 1 < DD) {
-                        base[r1 * rowlen + c1] = res[i].y;
-                        if (count) zeros += (unsigned)(res[i].y == 0.0);
-                    } else if (vi + 1 < NV) {
-                        A.load[(size_t)e * D + (vi + 1 - DD)] = res[i].y;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        rec[i] = Pr[i];
+                        rec[D + i] = Qr[i];
+                        rec[2 * D + i] = Ue[i];
+                        rec[3 * D + i] = Ve[i];
                     }
                 }
             }
-        }
-    }
-}
-
-// O warp, one row part: the off-diagonal block of the lane's item -> its slot in the row buffer
-template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void off_block(const AsmArgs& A, const unsigned char* __restrict__ sb, int lane, const LaneCtx& c,
-                                          const FaceGeo& g, const ElemBox& bxe, const ElemBox& bxo, double* __restrict__ outd,
-                                          int maxdepth, bool sync_before_store, unsigned& zeros) {
-    using DM = Dm<P, RS>;
-    constexpr int D = DM::D, RJ = DM::RJ, NB = DM::NB, J0 = PART * RJ;
-    double acc[NB];
+            eval_basis<P, DIFF>(x, y, bxo, A.lc, phi, gx, gy);
 #pragma unroll
-    for (int v = 0; v < NB; ++v) acc[v] = 0.0;
-    if (c.active) face_pass<P, RS, PART, DIFF, ADV, true>(A, sb, lane, g, c.sgn, c.down, bxe, bxo, acc);
-    if (sync_before_store) cta_sync(2);              // [B] the D warp is done with the partial buffer (= the row buffer)
-    double* dst0 = outd + c.ro + c.slot * D;
-    if (c.active && c.depth == 0) {
+            for (int i = 0; i < D; ++i) {
+                const double Vc = -Ws * phi[i];
+                double Uc = sg * Vc;
+                if (DIFF && gy_nz<P>(i)) Uc = fma(hw1, gy[i], Uc);
+                if (DIFF && gx_nz<P>(i)) Uc = fma(hw0, gx[i], Uc);
 #pragma unroll
-        for (int jj = 0; jj < RJ; ++jj) {
-            double* dst = dst0 + (J0 + jj) * c.rowlen;
-            if ((D & 1) == 0) {
-#pragma unroll
-                for (int i = 0; i < D; i += 2) reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(acc[jj * D + i], acc[jj * D + i + 1]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < D; ++i) dst[i] = acc[jj * D + i];
+                for (int jj = 0; jj < RJ; ++jj) {
+                    const int j = J0 + jj;
+                    double v = oacc[jj * D + i];
+                    v = fma(Pr[j], Uc, v);
+                    if (DIFF && (gx_nz<P>(j) || gy_nz<P>(j))) v = fma(Qr[j], Vc, v);
+                    oacc[jj * D + i] = v;
+                }
             }
         }
-        if (maxdepth == 0) zeros += count_zeros<NB>(acc);
-    }
-    // faces that repeat the previous neighbour add to its block, in item order
-    for (int dd = 1; dd <= maxdepth; ++dd) {
-        __syncwarp();
-        if (c.active && c.depth == dd) {
+        if (PART == 0) {
+            __syncwarp();                           // the records of point q are written
 #pragma unroll
-            for (int jj = 0; jj < RJ; ++jj) {
-                double* dst = dst0 + (J0 + jj) * c.rowlen;
+            for (int t = 0; t < NT; ++t) {
+                if (task[t].on) {
+                    for (int l = task[t].l0; l < task[t].l1; ++l) {      // items in adjacency order
+                        const double* rec = reinterpret_cast<const double*>(pquv + l * S::REC);
+                        const double Pj = rec[task[t].row], Qj = rec[D + task[t].row];
+                        if ((D & 1) == 0) {
 #pragma unroll
-                for (int i = 0; i < D; ++i) dst[i] += acc[jj * D + i];
+                            for (int i = 0; i < D; i += 2) {
+                                const double2 U = reinterpret_cast<const double2*>(rec + 2 * D)[i >> 1];
+                                const double2 V = reinterpret_cast<const double2*>(rec + 3 * D)[i >> 1];
+                                racc[t][i] = fma(Qj, V.x, fma(Pj, U.x, racc[t][i]));
+                                racc[t][i + 1] = fma(Qj, V.y, fma(Pj, U.y, racc[t][i + 1]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < D; ++i) racc[t][i] = fma(Qj, rec[3 * D + i], fma(Pj, rec[2 * D + i], racc[t][i]));
+                        }
+                    }
+                }
             }
+            __syncwarp();                           // the records may be overwritten by the next point
         }
     }
 }
 
 template <int P, int RS, bool DIFF, bool ADV>
-__global__ void __launch_bounds__(kFaceThreads) dg_face_kernel(const __grid_constant__ AsmArgs A) {
+__global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ AsmArgs A) {
     using DM = Dm<P, RS>;
     using S = FaceSmem<P, RS, DIFF, ADV>;
-    constexpr int D = DM::D, DD = DM::DD;
+    constexpr int D = DM::D, DD = DM::DD, NV = DM::NV, RJ = DM::RJ, NB = DM::NB, NT = S::NT, MAXE = S::MAXE;
     extern __shared__ __align__(128) unsigned char sm[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lane = threadIdx.x;
     const int e_beg = blockIdx.x * kWindow;
     const int e_end = min(e_beg + kWindow, A.g.n_rows);
     const int nw = e_end - e_beg;
     int* tab = reinterpret_cast<int*>(sm + S::OWIN);
     int *w_off = tab, *w_goff = tab + kTab, *w_sg = tab + 2 * kTab, *w_eg = tab + 3 * kTab, *w_round = tab + 4 * kTab;
     // ---- window tables + the rounds of the window ---------------------------------------------------------------------------
-    for (int i = tid; i <= nw; i += kFaceThreads) {
+    for (int i = lane; i <= nw; i += kWarp) {
         w_off[i] = A.adj_off[e_beg + i];
         w_goff[i] = A.grp_off[e_beg + i];
         w_sg[i] = A.g.elem_seg0 ? A.g.elem_seg0[e_beg + i] : e_beg + i;
         if (i < nw) w_eg[i] = gid_of(A, e_beg + i);
     }
-    __syncthreads();
-    if (warp == 0) {
-        int e = 0, nr = 0;
-        while (e < nw) {
-            if (lane == 0) w_round[nr] = e;
-            const int idx = e + lane;
-            const bool in = idx <= nw && lane <= kMaxE;
-            const int off = in ? w_off[idx] : 0, sg = in ? w_sg[idx] : 0;
-            const int k0 = __shfl_sync(kFull, off, 0), sg0 = __shfl_sync(kFull, sg, 0);
-            // an element is taken while the items fit one warp and the segments fit the staging buffer
-            const bool ok = in && lane >= 1 && (off - k0 <= kWarp) && (sg - sg0 <= kMaxSeg);
-            const unsigned m = __ballot_sync(kFull, ok) >> 1;
-            const int ne = __ffs(~m) - 1;          // length of the run of set bits (both conditions are monotone)
-            if (ne == 0) __trap();                 // more than 32 items / kMaxSeg segments in one element: rejected by the host entry
-            e += ne;
-            ++nr;
-        }
-        if (lane == 0) {
-            w_round[nr] = nw;
-            w_round[kTab - 1] = nr;
-        }
+    __syncwarp();
+    int nr = 0;
+    for (int e = 0; e < nw;) {
+        if (lane == 0) w_round[nr] = e;
+        const int idx = e + lane;
+        const bool in = idx <= nw && lane <= MAXE;
+        const int off = in ? w_off[idx] : 0, sg = in ? w_sg[idx] : 0;
+        const int k0 = __shfl_sync(kFull, off, 0), sg0 = __shfl_sync(kFull, sg, 0);
+        // an element is taken while the items fit one warp and the segments fit the staging buffer
+        const bool ok = in && lane >= 1 && (off - k0 <= kWarp) && (sg - sg0 <= kMaxSeg);
+        const unsigned m = __ballot_sync(kFull, ok) >> 1;
+        const int ne = __ffs(~m) - 1;              // length of the run of set bits (both conditions are monotone)
+        if (ne == 0) __trap();                     // more than 32 items / kMaxSeg segments in one element: rejected by the host entry
+        e += ne;
+        ++nr;
     }
-    __syncthreads();
-    const int nr = w_round[kTab - 1];
+    if (lane == 0) w_round[nr] = nw;
+    __syncwarp();
     unsigned zeros = 0;
+    unsigned char* sb = sm;
+    unsigned char* pquv = sm + S::OOUT;
 
-    Items it0 = load_items(A, tab, 0, lane), it1 = it0;
-    if (nr > 1) it1 = load_items(A, tab, 1, lane);
-    {
-        const Round x0 = load_round(tab, 0, lane);
-        stage_round<P, RS, DIFF, ADV>(A, sm, x0, it0, e_beg, warp, lane);
-    }
-    __pipeline_commit();
-    int buf = 0;
+    Items it = load_items(A, tab, 0, lane);
     for (int r = 0; r < nr; ++r) {
-        Items it2 = it1;
-        if (r + 2 < nr) it2 = load_items(A, tab, r + 2, lane);
-        if (r + 1 < nr) {
-            const Round xn = load_round(tab, r + 1, lane);
-            stage_round<P, RS, DIFF, ADV>(A, sm + (buf ^ 1) * S::STAGE, xn, it1, e_beg, warp, lane);
-        }
-        __pipeline_commit();
-        __pipeline_wait_prior(1);
-        cta_sync(1);                                // [A] the round's staging (copies of both warps) is visible
-        const unsigned char* sb = sm + buf * S::STAGE;
         const Round x = load_round(tab, r, lane);
-
-        // ---- decode the round (both warps) ---------------------------------------------------------------------------------------
-        LaneCtx c;
+        stage_round<P, RS, DIFF, ADV>(A, sb, x, it, e_beg, lane);
+        __pipeline_commit();
         const int nit = x.k1 - x.k0;
+        LaneCtx c;
         c.active = lane < nit;
-        c.elem_ls = x.off - x.k0;                  // lane i <= ne: first lane of element i
+        const int f = (it.item & 0x7fffffff) >> 1;
+        const unsigned upw = (c.active && A.c.if_upwind) ? A.c.if_upwind[f] : 0;
+        const int og = (c.active && A.g.elem_gid) ? A.g.elem_gid[it.nbr] : it.nbr;
+        const Items cur = it;
+        if (r + 1 < nr) it = load_items(A, tab, r + 1, lane);       // the next round's items arrive while this one computes
+
+        // ---- decode the round ----------------------------------------------------------------------------------------------------
+        const int elem_ls = x.off - x.k0;          // lane i <= ne: first lane of element i
         c.el = 0;
 #pragma unroll
-        for (int i = 1; i < kMaxE; ++i) {
-            const int o = __shfl_sync(kFull, c.elem_ls, i);
+        for (int i = 1; i < MAXE; ++i) {
+            const int o = __shfl_sync(kFull, elem_ls, i);
             if (i < x.ne && lane >= o) ++c.el;
         }
         if (!c.active) c.el = 0;
-        const int my_ls = __shfl_sync(kFull, c.elem_ls, c.el);
+        const int my_ls = __shfl_sync(kFull, elem_ls, c.el);
         const int eg = w_eg[x.e0 + c.el];
-        const bool headf = c.active && it0.item >= 0;
+        const bool headf = c.active && cur.item >= 0;
         const unsigned hm = __ballot_sync(kFull, headf);
         const unsigned below = (2u << lane) - 1u;
-        c.slot = __popc(hm & below & ~lowmask(my_ls)) - 1 + (it0.og > eg ? 1 : 0);
+        c.slot = __popc(hm & below & ~lowmask(my_ls)) - 1 + (og > eg ? 1 : 0);
         c.depth = c.active ? lane - (31 - __clz(hm & below)) : 0;
         const int maxdepth = A.has_dups ? __reduce_max_sync(kFull, c.depth) : 0;
-        const unsigned lm = __ballot_sync(kFull, headf && it0.og < eg);
-        const int ls_next = __shfl_down_sync(kFull, c.elem_ls, 1);
+        const unsigned lm = __ballot_sync(kFull, headf && og < eg);
+        const int ls_next = __shfl_down_sync(kFull, elem_ls, 1);
         const int goff_next = __shfl_down_sync(kFull, x.goff, 1);
-        c.elem_dslot = __popc(lm & lowmask(ls_next) & ~lowmask(c.elem_ls));
-        c.elem_ro = DD * ((x.goff - x.g0) + lane);
-        c.elem_rowlen = (goff_next - x.goff + 1) * D;
-        c.ro = __shfl_sync(kFull, c.elem_ro, c.el);
-        c.rowlen = __shfl_sync(kFull, c.elem_rowlen, c.el);
-        const int side = it0.item & 1;
+        const int elem_dslot = __popc(lm & lowmask(ls_next) & ~lowmask(elem_ls));
+        const int elem_ro = DD * ((x.goff - x.g0) + lane);
+        const int elem_rowlen = (goff_next - x.goff + 1) * D;
+        c.ro = __shfl_sync(kFull, elem_ro, c.el);
+        c.rowlen = __shfl_sync(kFull, elem_rowlen, c.el);
+        const int side = cur.item & 1;
         c.sgn = side ? -1.0 : 1.0;
-        c.down = A.c.if_upwind ? ((it0.upw != 0) == (side == 1)) : false;
+        c.down = A.c.if_upwind ? ((upw != 0) == (side == 1)) : false;
+        // row-owner tasks of this lane: (element, row) pairs in order
+        RowTask task[NT];
+        int t_s0[NT], t_s1[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int id = lane + t * kWarp;
+            const int el = id / D;
+            task[t].on = id < x.ne * D;
+            task[t].el = task[t].on ? el : 0;
+            task[t].row = id - el * D;
+            task[t].l0 = __shfl_sync(kFull, elem_ls, task[t].el);
+            task[t].l1 = __shfl_sync(kFull, elem_ls, task[t].el + 1);
+            task[t].ro = __shfl_sync(kFull, elem_ro, task[t].el);
+            task[t].rowlen = __shfl_sync(kFull, elem_rowlen, task[t].el);
+            task[t].dslot = __shfl_sync(kFull, elem_dslot, task[t].el);
+            t_s0[t] = __shfl_sync(kFull, x.sg, task[t].el) - x.sg0;
+            t_s1[t] = __shfl_sync(kFull, x.sg, task[t].el + 1) - x.sg0;
+        }
+        // first byte of the round's rows in the value array; the row buffer starts at the same 16-byte phase
+        double* gdst = A.data + (size_t)DD * ((size_t)x.g0 + e_beg + x.e0);
+        const int oshift = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
+        double* outd = reinterpret_cast<double*>(sm + S::OOUT + oshift);
+        const int ndbl = DD * ((x.g1 - x.g0) + x.ne);      // doubles of the round's rows
+
+        __pipeline_wait_prior(0);
+        if (lane == 0) bulk_wait_read();            // the previous round's bulk store has read the row buffer (= record buffer)
+        __syncwarp();
+
         FaceGeo g;
         {
             const unsigned char* p = sb + lane * 16;
@@ -770,47 +702,97 @@ __global__ void __launch_bounds__(kFaceThreads) dg_face_kernel(const __grid_cons
             g.midx = a.x; g.midy = a.y; g.tanx = b.x; g.tany = b.y; g.nx = cc.x; g.ny = cc.y; g.De = d.x; g.sigma = d.y;
         }
         const ElemBox bxe = lds_box(sb + S::OOWN + c.el * 64, 16);
-        // first byte of the round's rows in the value array; the row buffer starts at the same 16-byte phase
-        double* gdst = A.data + (size_t)DD * ((size_t)x.g0 + e_beg + x.e0);
-        const int oshift = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
-        double* outd = reinterpret_cast<double*>(sm + S::OOUT + oshift);
-        const int ndbl = DD * ((x.g1 - x.g0) + x.ne);      // doubles of the round's rows
-
-        if (warp == 0) {
-            // ---- D warp: diagonal contributions -> ordered sums -> diagonal blocks, load -----------------------------------------
-            double2 res[kMaxE];
-            diag_sums<P, RS, 0, DIFF, ADV>(A, sm, sb, lane, x, c, g, bxe, true, res);
-            cta_sync(2);                            // [B] all partials are read, the previous bulk store is done: rows may be written
-            diag_store<P, RS, 0, DIFF, ADV>(A, lane, x, c, e_beg + x.e0, outd, res, maxdepth == 0, zeros);
-            if (RS > 1) {
-                diag_sums<P, RS, RS - 1, DIFF, ADV>(A, sm, sb, lane, x, c, g, bxe, false, res);
-                diag_store<P, RS, RS - 1, DIFF, ADV>(A, lane, x, c, e_beg + x.e0, outd, res, maxdepth == 0, zeros);
+        const ElemBox bxo = lds_box(sb + 4 * 512 + lane * 16, 512);
+        // diagonal rows start from the volume sums (triangles first, main.py:315), the load is the volume sum itself
+        double racc[NT][D];
+        double lval[NT];
+        const double* vd = reinterpret_cast<const double*>(sb + S::OVD);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) racc[t][i] = 0.0;
+            lval[t] = 0.0;
+            if (task[t].on) {
+                for (int s = t_s0[t]; s < t_s1[t]; ++s) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) racc[t][i] += vd[(size_t)s * NV + task[t].row * D + i];
+                    lval[t] += vd[(size_t)s * NV + DD + task[t].row];
+                }
             }
-        } else {
-            // ---- O warp: off-diagonal blocks ---------------------------------------------------------------------------------------
-            const ElemBox bxo = lds_box(sb + 4 * 512 + lane * 16, 512);
-            off_block<P, RS, 0, DIFF, ADV>(A, sb, lane, c, g, bxe, bxo, outd, maxdepth, true, zeros);
-            if (RS > 1) off_block<P, RS, RS - 1, DIFF, ADV>(A, sb, lane, c, g, bxe, bxo, outd, maxdepth, false, zeros);
         }
-        fence_async_smem();
-        cta_sync(3);                                // [C] the rows of the round are complete
+        double oacc[NB];
+#pragma unroll
+        for (int v = 0; v < NB; ++v) oacc[v] = 0.0;
+        face_sweep<P, RS, 0, DIFF, ADV, NT>(A, sb, pquv, lane, c, g, bxe, bxo, task, oacc, racc);
+
+        // ---- rows of the round: off-diagonal blocks, diagonal rows, load -----------------------------------------------------------
+#pragma unroll
+        for (int part = 0; part < RS; ++part) {
+            if (part > 0) {
+#pragma unroll
+                for (int v = 0; v < NB; ++v) oacc[v] = 0.0;
+                face_sweep<P, RS, RS - 1, DIFF, ADV, NT>(A, sb, pquv, lane, c, g, bxe, bxo, task, oacc, racc);
+            }
+            double* dst0 = outd + c.ro + c.slot * D;
+            if (c.active && c.depth == 0) {
+#pragma unroll
+                for (int jj = 0; jj < RJ; ++jj) {
+                    double* dst = dst0 + (part * RJ + jj) * c.rowlen;
+                    if ((D & 1) == 0) {
+#pragma unroll
+                        for (int i = 0; i < D; i += 2) reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(oacc[jj * D + i], oacc[jj * D + i + 1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) dst[i] = oacc[jj * D + i];
+                    }
+                }
+                if (maxdepth == 0) zeros += count_zeros<NB>(reinterpret_cast<const double(&)[NB]>(*oacc));
+            }
+            // faces that repeat the previous neighbour add to its block, in item order
+            for (int dd = 1; dd <= maxdepth; ++dd) {
+                __syncwarp();
+                if (c.active && c.depth == dd) {
+#pragma unroll
+                    for (int jj = 0; jj < RJ; ++jj) {
+                        double* dst = dst0 + (part * RJ + jj) * c.rowlen;
+#pragma unroll
+                        for (int i = 0; i < D; ++i) dst[i] += oacc[jj * D + i];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (task[t].on) {
+                double* dst = outd + task[t].ro + task[t].row * task[t].rowlen + task[t].dslot * D;
+                if ((D & 1) == 0) {
+#pragma unroll
+                    for (int i = 0; i < D; i += 2) reinterpret_cast<double2*>(dst)[i >> 1] = make_double2(racc[t][i], racc[t][i + 1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) dst[i] = racc[t][i];
+                }
+                if (maxdepth == 0) zeros += count_zeros<D>(racc[t]);
+                A.load[(size_t)(e_beg + x.e0 + task[t].el) * D + task[t].row] = lval[t];
+            }
+        }
+        __syncwarp();
         if (maxdepth > 0) {
             // merged blocks: count the exact zeros of the finished rows (the per-lane counts above were skipped)
-            for (int w = tid; w < ndbl; w += kFaceThreads) zeros += (outd[w] == 0.0);
+            for (int w = lane; w < ndbl; w += kWarp) zeros += (outd[w] == 0.0);
         }
         // ---- one bulk store for all rows of the round ------------------------------------------------------------------------------
-        if (tid == 0) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
             int lo = 0, n = ndbl;
             if (oshift) { gdst[0] = outd[0]; lo = 1; --n; }
             const int core = n & ~1;
             if (core) bulk_s2g(gdst + lo, outd + lo, (uint32_t)core * 8);
             if (n & 1) gdst[lo + core] = outd[lo + core];
         }
-        it0 = it1;
-        it1 = it2;
-        buf ^= 1;
     }
-    if (tid == 0) bulk_wait_read();
+    if (lane == 0) bulk_wait_read();
     if (zeros) atomicAdd(A.zero_count, (unsigned long long)zeros);
 }
 
@@ -828,7 +810,7 @@ static int launch(const AsmArgs& A, cudaStream_t st) {
         RB_LAUNCH_CHECK("dg_volume_kernel");
     }
     const int blocks = (int)div_up(A.g.n_rows, kWindow);
-    fk<<<blocks, kFaceThreads, FS::TOTAL, st>>>(A);
+    fk<<<blocks, kWarp, FS::TOTAL, st>>>(A);
     RB_LAUNCH_CHECK("dg_face_kernel");
     return 0;
 }

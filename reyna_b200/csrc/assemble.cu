@@ -26,11 +26,16 @@ __device__ __forceinline__ double max_sub_area_g(const rb_geom& g, int e, double
     return kb;
 }
 
-__global__ void __launch_bounds__(256) dg_prepare_kernel(rb_geom g, const double* __restrict__ if_a_mid, double sigma_pp,
-                                                         double p2, ElemBox* __restrict__ ebox,
-                                                         FaceRec* __restrict__ frec) {
+// per-element basis scalings (needed by both assembly kernels)
+__global__ void __launch_bounds__(256) dg_prepare_boxes_kernel(rb_geom g, ElemBox* __restrict__ ebox) {
     const int stride = gridDim.x * blockDim.x;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.n_elem; e += stride) ebox[e] = make_box(g.bbox, e);
+}
+
+// per-face record: flattened geometry + SIPG penalty (needed by the face kernel only)
+__global__ void __launch_bounds__(256) dg_prepare_faces_kernel(rb_geom g, const double* __restrict__ if_a_mid, double sigma_pp,
+                                                               double p2, FaceRec* __restrict__ frec) {
+    const int stride = gridDim.x * blockDim.x;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.n_iface; f += stride) {
         const double2 P0 = reinterpret_cast<const double2*>(g.nodes)[g.iedge[2 * (size_t)f]];
         const double2 P1 = reinterpret_cast<const double2*>(g.nodes)[g.iedge[2 * (size_t)f + 1]];
@@ -58,7 +63,6 @@ __global__ void __launch_bounds__(256) dg_prepare_kernel(rb_geom g, const double
         frec[f] = r;
     }
 }
-
 
 }  // namespace rb
 
@@ -136,12 +140,12 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
     A.ebox = ebox;
     A.frec = frec;
     A.vdiag = reinterpret_cast<double*>(w);
-    {
-        const int64_t work = g->n_elem > g->n_iface ? g->n_elem : g->n_iface;
-        const int blocks = grid_for(work, 256, kNumSMs * 8);
-        dg_prepare_kernel<<<blocks, 256, 0, st>>>(*g, (diff && g->n_iface > 0) ? c->if_a_mid : nullptr, A.sigma_pp, A.p2,
-                                                 ebox, frec);
-        RB_LAUNCH_CHECK("dg_prepare_kernel");
+    dg_prepare_boxes_kernel<<<grid_for(g->n_elem, 256, kNumSMs * 8), 256, 0, st>>>(*g, ebox);
+    RB_LAUNCH_CHECK("dg_prepare_boxes_kernel");
+    if (g->n_iface > 0) {
+        dg_prepare_faces_kernel<<<grid_for(g->n_iface, 256, kNumSMs * 8), 256, 0, st>>>(
+            *g, diff ? c->if_a_mid : nullptr, A.sigma_pp, A.p2, frec);
+        RB_LAUNCH_CHECK("dg_prepare_faces_kernel");
     }
     return launch_assemble_items(A, p, diff, adv, st);
 }

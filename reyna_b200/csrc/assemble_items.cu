@@ -31,6 +31,7 @@ constexpr int kWarp = 32;
 constexpr int kMaxSeg = 8;      // volume segments staged per face round
 constexpr int kWindow = 64;     // consecutive elements per face CTA
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kVolAhead = 148 * 12;   // volume rounds resident on the GPU: the round that far ahead is prefetched into L2
 
 // ---- PTX: mbarrier + bulk async copies ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,6 +67,10 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t 
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -264,6 +269,13 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
         if (has_c) bulk_g2s(sm + S::OC, reinterpret_cast<const void*>(pc - hc), bc, bar);
         if (has_f) bulk_g2s(sm + S::OF, reinterpret_cast<const void*>(pf - hf), bf, bar);
     }
+    // the round that will take this slot of the GPU next: its samples are pulled into L2 below (its TMA then sees L2 latency)
+    const int rn = r + kVolAhead;
+    int u0 = 0, u1 = 0;
+    if (lane == 0 && rn < A.g.n_vrounds) {
+        u0 = A.g.vround_tri0[rn];
+        u1 = A.g.vround_tri0[rn + 1];
+    }
     __syncwarp();
     const bool active = lane < n;
     const int t = t0 + (active ? lane : 0);
@@ -288,6 +300,14 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
         if (lane == 0) s_start[nseg] = n;
     }
     mbar_wait(bar, 0);
+    if (u1 > u0) {
+        const uint32_t cn = (uint32_t)(QV * (u1 - u0));
+        const size_t fn = (size_t)QV * u0;
+        if (DIFF) bulk_prefetch_l2(A.c.vol_a + 4 * fn, cn * 32);
+        if (ADV) bulk_prefetch_l2(A.c.vol_b + 2 * fn, cn * 16);
+        if (has_c) bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(A.c.vol_c + fn) & ~(uintptr_t)15), (cn * 8 + 15) & ~15u);
+        if (has_f) bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(A.c.vol_f + fn) & ~(uintptr_t)15), (cn * 8 + 15) & ~15u);
+    }
     // |det(0.5*[V1-V0; V2-V0])| (full_assembly.py:40-41); the extra 0.5 is the `0.5 * z` of :75-77
     const double e1x = 0.5 * (V1.x - V0.x), e1y = 0.5 * (V1.y - V0.y);
     const double e2x = 0.5 * (V2.x - V0.x), e2y = 0.5 * (V2.y - V0.y);
@@ -320,10 +340,11 @@ struct FaceSmem {
     static constexpr int OOWN = PLANES;                          // own boxes of the round's elements [MAXE][64 bytes]
     static constexpr int OVD = OOWN + MAXE * 64;                 // volume sums of the round's segments [kMaxSeg][NV]
     static constexpr int STAGE = OVD + kMaxSeg * DM::NV * 8;     // the staging buffer
-    static constexpr int OOUT = STAGE;                           // block rows of the round (+ 16 bytes of alignment shift)
     static constexpr int OUTB = (32 + MAXE) * DM::DD * 8 + 16;
     static constexpr int REC = 4 * DM::D * 8 + 16;               // P, Q, U, V of one item at one point (+16: conflict-free lane stride)
-    static constexpr int PQUVB = 32 * REC;                       // lives in the row buffer until the rows are written
+    static constexpr int PQUVB = 32 * REC;
+    static constexpr int OOUT = STAGE;                           // block rows of the round (+ 16 bytes of alignment shift)
+    static constexpr int OPQ = OOUT;                             // the records live in the row buffer until the rows are written
     static constexpr int OWIN = OOUT + (OUTB > PQUVB ? OUTB : PQUVB);
     static constexpr int TOTAL = OWIN + 5 * kTab * 4;            // window tables: adj_off, grp_off, first segment, gid, rounds
     static_assert(STAGE % 16 == 0 && OUTB % 16 == 0 && REC % 16 == 0, "alignment");
@@ -371,7 +392,9 @@ __device__ __forceinline__ Items load_items(const AsmArgs& A, const int* __restr
     return it;
 }
 
-// cp.async staging of one round (everything an item needs, copied once)
+// cp.async staging of one round (everything an item needs, copied once).  (Fetching the per-item data into registers with
+// vector loads and writing the planes with 128-bit shared stores instead costs fewer shared-memory wavefronts -- a per-lane
+// cp.async gather lands lane by lane -- but was slower: profiles/r02_assemble_experiments.md.)
 template <int P, int RS, bool DIFF, bool ADV>
 __device__ __forceinline__ void stage_round(const AsmArgs& A, unsigned char* __restrict__ sb, const Round& x, const Items& it,
                                             int e_beg, int lane) {
@@ -419,17 +442,15 @@ __device__ __forceinline__ ElemBox lds_box(const unsigned char* p, int stride) {
     return b;
 }
 
-// exact zeros are rare: one FSETP per value on the high word (+-0 <=> high word is a float zero and the low word is 0;
-// a denormal with a zero high word only sends the caller to the exact count)
-__device__ __forceinline__ bool maybe_zero(double v) { return __int_as_float(__double2hiint(v)) == 0.0f; }
-
+// Exact zeros are rare: one FMNMX per value on the high word (v == +-0 <=> its high word, read as a float, is +-0 and the
+// low word is 0; a denormal with a zero high word only sends the caller to the exact count).
 template <int N>
 __device__ __forceinline__ unsigned count_zeros(const double (&v)[N]) {
-    bool any = false;
+    float m = 1.0f;
 #pragma unroll
-    for (int i = 0; i < N; ++i) any |= maybe_zero(v[i]);
+    for (int i = 0; i < N; ++i) m = fminf(m, fabsf(__int_as_float(__double2hiint(v[i]))));
     unsigned z = 0;
-    if (any) {
+    if (m == 0.0f) {
 #pragma unroll
         for (int i = 0; i < N; ++i) z += (v[i] == 0.0);
     }
@@ -461,8 +482,7 @@ struct RowTask {
 // off-diagonal part: columns from the neighbour's basis with the opposite sign).
 template <int P, int RS, int PART, bool DIFF, bool ADV, int NT>
 __device__ __forceinline__ void face_sweep(const AsmArgs& A, const unsigned char* __restrict__ sb, unsigned char* __restrict__ pquv,
-                                           int lane, const LaneCtx& c, const FaceGeo& g, const ElemBox& bxe, const ElemBox& bxo,
-                                           const RowTask (&task)[NT], double* __restrict__ oacc,
+                                           int lane, const LaneCtx& c, const RowTask (&task)[NT], double* __restrict__ oacc,
                                            double (&racc)[NT][Dm<P, RS>::D]) {
     using DM = Dm<P, RS>;
     using S = FaceSmem<P, RS, DIFF, ADV>;
@@ -470,6 +490,16 @@ __device__ __forceinline__ void face_sweep(const AsmArgs& A, const unsigned char
 #pragma unroll 1
     for (int q = 0; q < QE; ++q) {
         if (c.active) {
+            // face record and boxes are re-read from the staging buffer at every point: 48 registers less across the sweep
+            FaceGeo g;
+            {
+                const unsigned char* p = sb + lane * 16;
+                const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 512);
+                const double2 cc = *reinterpret_cast<const double2*>(p + 1024), d = *reinterpret_cast<const double2*>(p + 1536);
+                g.midx = a.x; g.midy = a.y; g.tanx = b.x; g.tany = b.y; g.nx = cc.x; g.ny = cc.y; g.De = d.x; g.sigma = d.y;
+            }
+            const ElemBox bxe = lds_box(sb + S::OOWN + c.el * 64, 16);
+            const ElemBox bxo = lds_box(sb + 4 * 512 + lane * 16, 512);
             double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
             if (DIFF) {
                 const double2 r0 = *reinterpret_cast<const double2*>(sb + (8 + 2 * q) * 512 + lane * 16);
@@ -510,7 +540,7 @@ __device__ __forceinline__ void face_sweep(const AsmArgs& A, const unsigned char
                 }
             }
             if (PART == 0) {
-                // the item's record for the row owners: P, Q, then U, V of the diagonal part
+                // the item's record for the row owners: (P_j, Q_j) pairs, then (U_i, V_i) pairs of the diagonal part
                 double* rec = reinterpret_cast<double*>(pquv + lane * S::REC);
                 double Ue[D], Ve[D];
 #pragma unroll
@@ -520,22 +550,10 @@ __device__ __forceinline__ void face_sweep(const AsmArgs& A, const unsigned char
                     if (DIFF && gy_nz<P>(i)) Ue[i] = fma(hw1, gy[i], Ue[i]);
                     if (DIFF && gx_nz<P>(i)) Ue[i] = fma(hw0, gx[i], Ue[i]);
                 }
-                if ((D & 1) == 0) {
 #pragma unroll
-                    for (int i = 0; i < D; i += 2) {
-                        reinterpret_cast<double2*>(rec)[i >> 1] = make_double2(Pr[i], Pr[i + 1]);
-                        reinterpret_cast<double2*>(rec + D)[i >> 1] = make_double2(Qr[i], Qr[i + 1]);
-                        reinterpret_cast<double2*>(rec + 2 * D)[i >> 1] = make_double2(Ue[i], Ue[i + 1]);
-                        reinterpret_cast<double2*>(rec + 3 * D)[i >> 1] = make_double2(Ve[i], Ve[i + 1]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < D; ++i) {
-                        rec[i] = Pr[i];
-                        rec[D + i] = Qr[i];
-                        rec[2 * D + i] = Ue[i];
-                        rec[3 * D + i] = Ve[i];
-                    }
+                for (int i = 0; i < D; ++i) {
+                    reinterpret_cast<double2*>(rec)[i] = make_double2(Pr[i], Qr[i]);
+                    reinterpret_cast<double2*>(rec)[D + i] = make_double2(Ue[i], Ve[i]);
                 }
             }
             eval_basis<P, DIFF>(x, y, bxo, A.lc, phi, gx, gy);
@@ -561,20 +579,13 @@ __device__ __forceinline__ void face_sweep(const AsmArgs& A, const unsigned char
             for (int t = 0; t < NT; ++t) {
                 if (task[t].on) {
                     for (int l = task[t].l0; l < task[t].l1; ++l) {      // items in adjacency order
-                        const double* rec = reinterpret_cast<const double*>(pquv + l * S::REC);
-                        const double Pj = rec[task[t].row], Qj = rec[D + task[t].row];
-                        if ((D & 1) == 0) {
+                        const double2* rec = reinterpret_cast<const double2*>(pquv + l * S::REC);
+                        const double2 pq = rec[task[t].row];
+                        double2 uv[D];
 #pragma unroll
-                            for (int i = 0; i < D; i += 2) {
-                                const double2 U = reinterpret_cast<const double2*>(rec + 2 * D)[i >> 1];
-                                const double2 V = reinterpret_cast<const double2*>(rec + 3 * D)[i >> 1];
-                                racc[t][i] = fma(Qj, V.x, fma(Pj, U.x, racc[t][i]));
-                                racc[t][i + 1] = fma(Qj, V.y, fma(Pj, U.y, racc[t][i + 1]));
-                            }
-                        } else {
+                        for (int i = 0; i < D; ++i) uv[i] = rec[D + i];
 #pragma unroll
-                            for (int i = 0; i < D; ++i) racc[t][i] = fma(Qj, rec[3 * D + i], fma(Pj, rec[2 * D + i], racc[t][i]));
-                        }
+                        for (int i = 0; i < D; ++i) racc[t][i] = fma(pq.y, uv[i].y, fma(pq.x, uv[i].x, racc[t][i]));
                     }
                 }
             }
@@ -622,21 +633,34 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
     __syncwarp();
     unsigned zeros = 0;
     unsigned char* sb = sm;
-    unsigned char* pquv = sm + S::OOUT;
+    unsigned char* pquv = sm + S::OPQ;
 
-    Items it = load_items(A, tab, 0, lane);
+    // items of round r are fetched two rounds ahead (registers), its face data one round ahead (cp.async, issued as soon as
+    // the sweep of round r-1 has consumed the staging buffer)
+    Items cur = load_items(A, tab, 0, lane), nxt = cur;
+    if (nr > 1) nxt = load_items(A, tab, 1, lane);
+    unsigned upw = 0;
+    int og = 0;
+    {
+        const Round x0 = load_round(tab, 0, lane);
+        stage_round<P, RS, DIFF, ADV>(A, sb, x0, cur, e_beg, lane);
+        __pipeline_commit();
+        if (lane < x0.k1 - x0.k0) {
+            if (A.c.if_upwind) upw = A.c.if_upwind[(cur.item & 0x7fffffff) >> 1];
+            og = A.g.elem_gid ? A.g.elem_gid[cur.nbr] : cur.nbr;
+        }
+    }
+    int t_el[NT], t_row[NT];                        // row-owner tasks of this lane: (element of the round, row), in order
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        t_el[t] = (lane + t * kWarp) / D;
+        t_row[t] = (lane + t * kWarp) - t_el[t] * D;
+    }
     for (int r = 0; r < nr; ++r) {
         const Round x = load_round(tab, r, lane);
-        stage_round<P, RS, DIFF, ADV>(A, sb, x, it, e_beg, lane);
-        __pipeline_commit();
         const int nit = x.k1 - x.k0;
         LaneCtx c;
         c.active = lane < nit;
-        const int f = (it.item & 0x7fffffff) >> 1;
-        const unsigned upw = (c.active && A.c.if_upwind) ? A.c.if_upwind[f] : 0;
-        const int og = (c.active && A.g.elem_gid) ? A.g.elem_gid[it.nbr] : it.nbr;
-        const Items cur = it;
-        if (r + 1 < nr) it = load_items(A, tab, r + 1, lane);       // the next round's items arrive while this one computes
 
         // ---- decode the round ----------------------------------------------------------------------------------------------------
         const int elem_ls = x.off - x.k0;          // lane i <= ne: first lane of element i
@@ -671,11 +695,9 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
         int t_s0[NT], t_s1[NT];
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            const int id = lane + t * kWarp;
-            const int el = id / D;
-            task[t].on = id < x.ne * D;
-            task[t].el = task[t].on ? el : 0;
-            task[t].row = id - el * D;
+            task[t].on = t_el[t] < x.ne;
+            task[t].el = task[t].on ? t_el[t] : 0;
+            task[t].row = t_row[t];
             task[t].l0 = __shfl_sync(kFull, elem_ls, task[t].el);
             task[t].l1 = __shfl_sync(kFull, elem_ls, task[t].el + 1);
             task[t].ro = __shfl_sync(kFull, elem_ro, task[t].el);
@@ -694,15 +716,6 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
         if (lane == 0) bulk_wait_read();            // the previous round's bulk store has read the row buffer (= record buffer)
         __syncwarp();
 
-        FaceGeo g;
-        {
-            const unsigned char* p = sb + lane * 16;
-            const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 512);
-            const double2 cc = *reinterpret_cast<const double2*>(p + 1024), d = *reinterpret_cast<const double2*>(p + 1536);
-            g.midx = a.x; g.midy = a.y; g.tanx = b.x; g.tany = b.y; g.nx = cc.x; g.ny = cc.y; g.De = d.x; g.sigma = d.y;
-        }
-        const ElemBox bxe = lds_box(sb + S::OOWN + c.el * 64, 16);
-        const ElemBox bxo = lds_box(sb + 4 * 512 + lane * 16, 512);
         // diagonal rows start from the volume sums (triangles first, main.py:315), the load is the volume sum itself
         double racc[NT][D];
         double lval[NT];
@@ -723,7 +736,7 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
         double oacc[NB];
 #pragma unroll
         for (int v = 0; v < NB; ++v) oacc[v] = 0.0;
-        face_sweep<P, RS, 0, DIFF, ADV, NT>(A, sb, pquv, lane, c, g, bxe, bxo, task, oacc, racc);
+        face_sweep<P, RS, 0, DIFF, ADV, NT>(A, sb, pquv, lane, c, task, oacc, racc);
 
         // ---- rows of the round: off-diagonal blocks, diagonal rows, load -----------------------------------------------------------
 #pragma unroll
@@ -731,8 +744,21 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
             if (part > 0) {
 #pragma unroll
                 for (int v = 0; v < NB; ++v) oacc[v] = 0.0;
-                face_sweep<P, RS, RS - 1, DIFF, ADV, NT>(A, sb, pquv, lane, c, g, bxe, bxo, task, oacc, racc);
+                face_sweep<P, RS, RS - 1, DIFF, ADV, NT>(A, sb, pquv, lane, c, task, oacc, racc);
+                __syncwarp();
             }
+            if (part == RS - 1 && r + 1 < nr) {
+                // the staging buffer is consumed: the next round's face data starts travelling while the rows are written
+                const Round xn = load_round(tab, r + 1, lane);
+                stage_round<P, RS, DIFF, ADV>(A, sb, xn, nxt, e_beg, lane);
+                if (lane < xn.k1 - xn.k0) {
+                    if (A.c.if_upwind) upw = A.c.if_upwind[(nxt.item & 0x7fffffff) >> 1];
+                    og = A.g.elem_gid ? A.g.elem_gid[nxt.nbr] : nxt.nbr;
+                }
+                cur = nxt;
+                if (r + 2 < nr) nxt = load_items(A, tab, r + 2, lane);
+            }
+            if (part == RS - 1) __pipeline_commit();
             double* dst0 = outd + c.ro + c.slot * D;
             if (c.active && c.depth == 0) {
 #pragma unroll

@@ -262,28 +262,13 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     n_dof_total = geo.n_elements * ((p + 1) * (p + 2) // 2)
     d = (p + 1) * (p + 2) // 2
 
-    # pinned landing buffers for the device->host read of the result
-    host_out = {}
-
-    def read_back(dv):
-        nbytes = 0
-        for k in ("indptr", "indices", "data", "load"):
-            t = dv[k]
-            buf = host_out.get(k)
-            if buf is None or buf.shape != t.shape:
-                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                host_out[k] = buf
-            buf.copy_(t, non_blocking=True)
-            nbytes += t.numel() * t.element_size()
-        torch.cuda.current_stream().synchronize()
-        return nbytes
-
-    # ---- e2e: DGFEM.dgfem(solve=False) from host data, result read back ------------------------------------------------
+    # ---- e2e: DGFEM.dgfem(solve=False) from host data; the result (indptr, indices, data, load) lands in pinned host memory
+    # inside the call (download_result: evaluate | upload | assemble | download are pipelined chunk by chunk) -----------------
+    dg.download_result = True
     first_call_s = None
     for _ in range(args.warmup):
         tf = time.perf_counter()
         dg.dgfem(solve=False)
-        read_back(dg._dev)
         if first_call_s is None:          # includes quadrature-point generation, pinned allocation, geometry upload
             first_call_s = time.perf_counter() - tf
     barrier()
@@ -293,11 +278,14 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     d2h = 0
     for _ in range(args.steps):
         dg.dgfem(solve=False)
-        d2h = read_back(dg._dev)
+        d2h = int(dg.timings["d2h_bytes"])
+        assert dg._host is not None and dg._host["data"].shape[0] == dg._dev["data"].shape[0]
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps
     h2d = int(dg.timings.get("h2d_bytes", 0))
     e2e_breakdown = {k: v for k, v in dg.timings.items() if k.endswith("_s")}
+    dg.download_result = False
+    dg._host = None
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

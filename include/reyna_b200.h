@@ -147,6 +147,17 @@ size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface, int32_t n_
 int reyna_b200_assemble(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
                         double sigma_D, double *data, double *load, long long *zero_count, void *workspace,
                         size_t workspace_bytes, void *stream);
+/* The same assembly in two steps, for callers that pipeline the host evaluation of the volume coefficients with the
+ * device work (DGFEM.dgfem evaluates the user's callables chunk by chunk): reyna_b200_assemble_prepare() runs the
+ * geometry / penalty prepass (it needs the FACE samples only), reyna_b200_assemble_range() then assembles the block rows
+ * of elements [elem_lo, elem_hi) = volume rounds [vround_lo, vround_hi) (a range of WHOLE rounds of rb_geom.vround_tri0),
+ * reading only the volume samples of those rounds.  reyna_b200_assemble() == prepare + range over everything. */
+int reyna_b200_assemble_prepare(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
+                                double sigma_D, void *workspace, size_t workspace_bytes, void *stream);
+int reyna_b200_assemble_range(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
+                              double sigma_D, double *data, double *load, long long *zero_count, void *workspace,
+                              size_t workspace_bytes, int32_t elem_lo, int32_t elem_hi, int32_t vround_lo,
+                              int32_t vround_hi, void *stream);
 
 /* Boundary faces: elliptic (Dirichlet SIPG) and inflow terms subtracted in place from the diagonal blocks and the
  * load (replaces _diffusion_bcs_contribution / _advection_bcs_contribution, main.py:376-474, and

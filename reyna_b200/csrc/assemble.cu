@@ -77,35 +77,26 @@ extern "C" size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface,
     return align16(sizeof(ElemBox) * ne) + align16(sizeof(FaceRec) * nf) + align16(sizeof(double) * ns * (d * d + d)) + 256;
 }
 
-extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
-                                   double sigma_D, double* data, double* load, long long* zero_count, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
-    RB_REQUIRE(g && s && c && q && data && load && zero_count && workspace, RB_E_ARG, "reyna_b200_assemble: null argument");
+// Shared argument check + kernel argument block of the three entry points below.
+static int make_args(const char* who, const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q, double sigma_D,
+                     double* data, double* load, long long* zero_count, void* workspace, size_t workspace_bytes, AsmArgs& A,
+                     bool& diff, bool& adv) {
+    (void)who;
+    RB_REQUIRE(g && s && c && q && workspace, RB_E_ARG, "reyna_b200_assemble: null argument");
     const int p = q->p;
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_assemble: polynomial degree must be 1..3");
     const int n_vsegs = g->elem_seg0 ? g->n_vsegs : g->n_rows;
     RB_REQUIRE(workspace_bytes >= reyna_b200_assemble_workspace(g->n_elem, g->n_iface, n_vsegs, p), RB_E_WORKSPACE,
                "reyna_b200_assemble: workspace too small");
-    const bool diff = c->vol_a != nullptr, adv = c->vol_b != nullptr;
+    // which terms are present is decided by the FACE samples when there are faces (the volume samples may still be on their
+    // way to the device when the prepass runs)
+    diff = c->vol_a != nullptr || c->if_a != nullptr;
+    adv = c->vol_b != nullptr || c->if_b != nullptr;
     RB_REQUIRE(diff || adv, RB_E_NOCOEF, "reyna_b200_assemble: no advection or diffusion specified");
     RB_REQUIRE(!diff || (c->if_a && c->if_a_mid) || g->n_iface == 0, RB_E_ARG,
                "reyna_b200_assemble: diffusion given without interior-face samples");
     RB_REQUIRE(!adv || (c->if_b && c->if_upwind) || g->n_iface == 0, RB_E_ARG,
                "reyna_b200_assemble: advection given without interior-face samples / upwind flags");
-    if (g->n_rows == 0) return 0;
-    RB_REQUIRE(g->n_tri == 0 || (g->tri_xy && g->vround_tri0 && g->n_vrounds > 0), RB_E_ARG,
-               "reyna_b200_assemble: the geometry carries no volume stream (rb_geom.tri_xy / vround_tri0)");
-    RB_REQUIRE((g->tri_seg == nullptr) == (g->elem_seg0 == nullptr), RB_E_ARG,
-               "reyna_b200_assemble: tri_seg and elem_seg0 must be given together");
-    RB_REQUIRE(s->max_items <= items_max_face_items(), RB_E_ARG,
-               "reyna_b200_assemble: an element has more than 32 contributing interior faces");
-    RB_REQUIRE(((uintptr_t)data & 15) == 0 && ((uintptr_t)load & 7) == 0, RB_E_ARG, "reyna_b200_assemble: data must be 16-byte aligned");
-    RB_REQUIRE((!c->vol_a || ((uintptr_t)c->vol_a & 15) == 0) && (!c->vol_b || ((uintptr_t)c->vol_b & 15) == 0) &&
-                   (!c->vol_c || ((uintptr_t)c->vol_c & 15) == 0) && (!c->vol_f || ((uintptr_t)c->vol_f & 15) == 0) &&
-                   (!g->tri_xy || ((uintptr_t)g->tri_xy & 15) == 0),
-               RB_E_ARG, "reyna_b200_assemble: volume sample arrays must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    AsmArgs A;
     memset(&A, 0, sizeof(A));
     A.g = *g;
     A.adj_off = s->adj_off;
@@ -133,19 +124,91 @@ extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, cons
     // prepass tables and the volume sums (16-byte aligned slices of the workspace)
     const size_t ne = (size_t)(g->n_elem > 0 ? g->n_elem : 1), nf = (size_t)(g->n_iface > 0 ? g->n_iface : 1);
     uintptr_t w = ((uintptr_t)workspace + 15) & ~(uintptr_t)15;
-    ElemBox* ebox = reinterpret_cast<ElemBox*>(w);
+    A.ebox = reinterpret_cast<ElemBox*>(w);
     w += align16(sizeof(ElemBox) * ne);
-    FaceRec* frec = reinterpret_cast<FaceRec*>(w);
+    A.frec = reinterpret_cast<FaceRec*>(w);
     w += align16(sizeof(FaceRec) * nf);
-    A.ebox = ebox;
-    A.frec = frec;
     A.vdiag = reinterpret_cast<double*>(w);
-    dg_prepare_boxes_kernel<<<grid_for(g->n_elem, 256, kNumSMs * 8), 256, 0, st>>>(*g, ebox);
+    return 0;
+}
+
+static int run_prepare(const AsmArgs& A, bool diff, cudaStream_t st) {
+    const rb_geom& g = A.g;
+    dg_prepare_boxes_kernel<<<grid_for(g.n_elem, 256, kNumSMs * 8), 256, 0, st>>>(g, const_cast<ElemBox*>(A.ebox));
     RB_LAUNCH_CHECK("dg_prepare_boxes_kernel");
-    if (g->n_iface > 0) {
-        dg_prepare_faces_kernel<<<grid_for(g->n_iface, 256, kNumSMs * 8), 256, 0, st>>>(
-            *g, diff ? c->if_a_mid : nullptr, A.sigma_pp, A.p2, frec);
+    if (g.n_iface > 0) {
+        dg_prepare_faces_kernel<<<grid_for(g.n_iface, 256, kNumSMs * 8), 256, 0, st>>>(g, diff ? A.c.if_a_mid : nullptr, A.sigma_pp,
+                                                                                       A.p2, const_cast<FaceRec*>(A.frec));
         RB_LAUNCH_CHECK("dg_prepare_faces_kernel");
     }
+    return 0;
+}
+
+static int run_range(AsmArgs& A, const rb_structure* s, int p, bool diff, bool adv, int elem_lo, int elem_hi, int vround_lo,
+                     int vround_hi, cudaStream_t st) {
+    const rb_geom& g = A.g;
+    RB_REQUIRE(A.data && A.load && A.zero_count, RB_E_ARG, "reyna_b200_assemble: null output");
+    RB_REQUIRE(0 <= elem_lo && elem_lo <= elem_hi && elem_hi <= g.n_rows && 0 <= vround_lo && vround_lo <= vround_hi &&
+                   vround_hi <= g.n_vrounds,
+               RB_E_ARG, "reyna_b200_assemble: invalid element / volume-round range");
+    if (elem_lo == elem_hi) return 0;
+    RB_REQUIRE(!diff || A.c.vol_a, RB_E_ARG, "reyna_b200_assemble: diffusion without volume samples");
+    RB_REQUIRE(!adv || A.c.vol_b, RB_E_ARG, "reyna_b200_assemble: advection without volume samples");
+    RB_REQUIRE(g.n_tri == 0 || (g.tri_xy && g.vround_tri0 && g.n_vrounds > 0), RB_E_ARG,
+               "reyna_b200_assemble: the geometry carries no volume stream (rb_geom.tri_xy / vround_tri0)");
+    RB_REQUIRE((g.tri_seg == nullptr) == (g.elem_seg0 == nullptr), RB_E_ARG,
+               "reyna_b200_assemble: tri_seg and elem_seg0 must be given together");
+    RB_REQUIRE(s->max_items <= items_max_face_items(), RB_E_ARG,
+               "reyna_b200_assemble: an element has more than 32 contributing interior faces");
+    RB_REQUIRE(((uintptr_t)A.data & 15) == 0 && ((uintptr_t)A.load & 7) == 0, RB_E_ARG,
+               "reyna_b200_assemble: data must be 16-byte aligned");
+    const rb_coefs& c = A.c;
+    RB_REQUIRE((!c.vol_a || ((uintptr_t)c.vol_a & 15) == 0) && (!c.vol_b || ((uintptr_t)c.vol_b & 15) == 0) &&
+                   (!c.vol_c || ((uintptr_t)c.vol_c & 15) == 0) && (!c.vol_f || ((uintptr_t)c.vol_f & 15) == 0) &&
+                   (!g.tri_xy || ((uintptr_t)g.tri_xy & 15) == 0),
+               RB_E_ARG, "reyna_b200_assemble: volume sample arrays must be 16-byte aligned");
+    A.elem_lo = elem_lo;
+    A.elem_hi = elem_hi;
+    A.vround_lo = vround_lo;
+    A.vround_hi = vround_hi;
     return launch_assemble_items(A, p, diff, adv, st);
+}
+
+extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
+                                   double sigma_D, double* data, double* load, long long* zero_count, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    RB_REQUIRE(data && load && zero_count, RB_E_ARG, "reyna_b200_assemble: null argument");
+    AsmArgs A;
+    bool diff, adv;
+    int rc = make_args("reyna_b200_assemble", g, s, c, q, sigma_D, data, load, zero_count, workspace, workspace_bytes, A, diff, adv);
+    if (rc) return rc;
+    if (g->n_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = run_prepare(A, diff, st);
+    if (rc) return rc;
+    return run_range(A, s, q->p, diff, adv, 0, g->n_rows, 0, g->n_vrounds, st);
+}
+
+extern "C" int reyna_b200_assemble_prepare(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
+                                           double sigma_D, void* workspace, size_t workspace_bytes, void* stream) {
+    AsmArgs A;
+    bool diff, adv;
+    int rc = make_args("reyna_b200_assemble_prepare", g, s, c, q, sigma_D, nullptr, nullptr, nullptr, workspace, workspace_bytes, A,
+                       diff, adv);
+    if (rc) return rc;
+    if (g->n_rows == 0) return 0;
+    return run_prepare(A, diff, (cudaStream_t)stream);
+}
+
+extern "C" int reyna_b200_assemble_range(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
+                                         double sigma_D, double* data, double* load, long long* zero_count, void* workspace,
+                                         size_t workspace_bytes, int32_t elem_lo, int32_t elem_hi, int32_t vround_lo,
+                                         int32_t vround_hi, void* stream) {
+    RB_REQUIRE(data && load && zero_count, RB_E_ARG, "reyna_b200_assemble_range: null argument");
+    AsmArgs A;
+    bool diff, adv;
+    int rc = make_args("reyna_b200_assemble_range", g, s, c, q, sigma_D, data, load, zero_count, workspace, workspace_bytes, A, diff,
+                       adv);
+    if (rc) return rc;
+    return run_range(A, s, q->p, diff, adv, elem_lo, elem_hi, vround_lo, vround_hi, (cudaStream_t)stream);
 }

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
     constexpr int QV = DM::QV;
     extern __shared__ __align__(128) unsigned char sm[];
     const int lane = threadIdx.x;
-    const int r = blockIdx.x;
+    const int r = A.vround_lo + blockIdx.x;
     const int t0 = A.g.vround_tri0[r];
     const int n = A.g.vround_tri0[r + 1] - t0;
     const bool has_c = A.c.vol_c != nullptr, has_f = A.c.vol_f != nullptr;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
     // the round that will take this slot of the GPU next: its samples are pulled into L2 below (its TMA then sees L2 latency)
     const int rn = r + kVolAhead;
     int u0 = 0, u1 = 0;
-    if (lane == 0 && rn < A.g.n_vrounds) {
+    if (lane == 0 && rn < A.vround_hi) {
         u0 = A.g.vround_tri0[rn];
         u1 = A.g.vround_tri0[rn + 1];
     }
@@ -601,8 +601,8 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
     constexpr int D = DM::D, DD = DM::DD, NV = DM::NV, RJ = DM::RJ, NB = DM::NB, NT = S::NT, MAXE = S::MAXE;
     extern __shared__ __align__(128) unsigned char sm[];
     const int lane = threadIdx.x;
-    const int e_beg = blockIdx.x * kWindow;
-    const int e_end = min(e_beg + kWindow, A.g.n_rows);
+    const int e_beg = A.elem_lo + blockIdx.x * kWindow;
+    const int e_end = min(e_beg + kWindow, A.elem_hi);
     const int nw = e_end - e_beg;
     int* tab = reinterpret_cast<int*>(sm + S::OWIN);
     int *w_off = tab, *w_goff = tab + kTab, *w_sg = tab + 2 * kTab, *w_eg = tab + 3 * kTab, *w_round = tab + 4 * kTab;
@@ -831,11 +831,11 @@ static int launch(const AsmArgs& A, cudaStream_t st) {
     auto fk = dg_face_kernel<P, RS, DIFF, ADV>;
     RB_CUDA(cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS::TOTAL));
     RB_CUDA(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS::TOTAL));
-    if (A.g.n_vrounds > 0) {
-        vk<<<A.g.n_vrounds, kWarp, VS::TOTAL, st>>>(A);
+    if (A.vround_hi > A.vround_lo) {
+        vk<<<A.vround_hi - A.vround_lo, kWarp, VS::TOTAL, st>>>(A);
         RB_LAUNCH_CHECK("dg_volume_kernel");
     }
-    const int blocks = (int)div_up(A.g.n_rows, kWindow);
+    const int blocks = (int)div_up(A.elem_hi - A.elem_lo, kWindow);
     fk<<<blocks, kWarp, FS::TOTAL, st>>>(A);
     RB_LAUNCH_CHECK("dg_face_kernel");
     return 0;

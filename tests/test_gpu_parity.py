@@ -332,3 +332,94 @@ def test_repeated_neighbours_merge_into_one_block(rb, name, p):
     assert bad == 0 and max_rel <= util.TOL_ENTRY
     assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
     assert util.rel_l2(dg.solution, dg_oracle.solve(B, L)) <= util.TOL_SOLUTION
+
+
+@pytest.mark.parametrize("name,p,chunk", [("adr", 2, 700), ("variable", 3, 1500), ("variable_hyperbolic", 1, 333),
+                                          ("variable", 2, 10 ** 9)])
+def test_pipelined_download_equals_lazy_materialisation(rb, name, p, chunk):
+    """dgfem() with ``download_result`` (volume samples evaluated / uploaded / assembled / downloaded chunk by chunk on three
+    streams) leaves, in host memory, bitwise the system a plain dgfem() + lazy ``B`` / ``L`` gives."""
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(4096, tiles=4, seed=5), subtriangulation="fan")
+    ref = _run(rb, geo, name, p, solve=False)
+    dg = rb.DGFEM(geo, polynomial_degree=p)
+    dg.add_data(**PROBLEMS[name]["data"])
+    dg.download_result = True
+    dg.pipeline_chunk_elements = chunk
+    for _ in range(2):                       # the second call reuses the pinned staging buffers
+        dg.dgfem(solve=False)
+        assert dg._host is not None
+        assert np.array_equal(dg.B.indptr, ref.B.indptr) and np.array_equal(dg.B.indices, ref.B.indices)
+        assert np.array_equal(dg.B.data, ref.B.data)
+        assert np.array_equal(np.asarray(dg.L.todense()), np.asarray(ref.L.todense()))
+
+
+def _fan_mesh(rb, n_spokes):
+    """One polygon with ``n_spokes`` + 3 vertices (a disc sector) surrounded by ``n_spokes`` thin neighbours: the centre element
+    has many interior faces and many sub-triangles (volume segments, rounds of its own)."""
+    th = np.linspace(0.0, 0.5 * np.pi, n_spokes + 1)
+    inner = np.column_stack((0.5 * np.cos(th), 0.5 * np.sin(th)))
+    outer = np.column_stack((np.cos(th), np.sin(th)))
+    v = np.vstack(([[0.0, 0.0]], inner, outer))
+    ni = n_spokes + 1
+    regions = [np.concatenate(([0], 1 + np.arange(ni)))]
+    pts = [[0.2, 0.2]]
+    for k in range(n_spokes):
+        regions.append(np.array([1 + k, 1 + ni + k, 1 + ni + k + 1, 1 + k + 1]))
+        pts.append(list(0.25 * (inner[k] + inner[k + 1] + outer[k] + outer[k + 1])))
+    return rb.PolyMesh(v, regions, np.array(pts), None)
+
+
+@pytest.mark.parametrize("n_spokes,name,p", [(20, "variable", 2), (31, "adr", 1), (31, "variable", 3), (29, "variable_hyperbolic", 2)])
+def test_element_with_many_faces_and_triangles(rb, n_spokes, name, p):
+    """A polygon with up to 31 neighbours / 32 sub-triangles (the limits of one warp round) next to small elements."""
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(_fan_mesh(rb, n_spokes))
+    dg = _run(rb, geo, name, p, solve=False)
+    B, L, info = dg_oracle.assemble(geo, p, **PROBLEMS[name]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
+
+
+def test_element_with_more_than_32_triangles_uses_segments(rb):
+    """More than 32 sub-triangles in one element: its volume rounds are summed through segments."""
+    from oracle import dg_oracle
+    from reyna_b200.sampling import volume_stream_of
+    geo = rb.DGFEMGeometry(_fan_mesh(rb, 30), subtriangulation="fan")
+    # refine the sub-triangulation of element 0 artificially: split every triangle of it in two (same quadrature exactness)
+    fg = rb.flat_geometry(geo)
+    t0, t1 = int(fg.tri_off[0]), int(fg.tri_off[1])
+    assert t1 - t0 >= 29
+    nodes = np.asarray(geo.nodes, dtype=float)
+    tri = np.asarray(geo.subtriangulation).reshape(-1, 3)
+    new_nodes, new_tri = [nodes], []
+    nn = nodes.shape[0]
+    for t in range(t0, t1):
+        a, b, c = tri[t]
+        new_nodes.append(0.5 * (nodes[b] + nodes[c])[None, :])
+        new_tri += [[a, b, nn], [a, nn, c]]
+        nn += 1
+    geo.nodes = np.vstack(new_nodes)
+    geo.mesh.vertices = geo.nodes
+    geo.subtriangulation = np.vstack((np.array(new_tri), tri[t1:]))
+    geo.triangle_to_polygon = np.concatenate((np.zeros(len(new_tri), dtype=int), np.asarray(geo.triangle_to_polygon)[t1:]))
+    geo.n_triangles = geo.subtriangulation.shape[0]
+    geo.n_nodes = geo.nodes.shape[0]
+    for attr in ("_rb_flat", "_rb_dev", "_rb_points"):
+        if hasattr(geo, attr):
+            delattr(geo, attr)
+    vs = volume_stream_of(rb.flat_geometry(geo))
+    assert vs.tri_seg is not None and vs.n_segs > geo.n_elements
+    dg = _run(rb, geo, "variable", 2, solve=False)
+    B, L, info = dg_oracle.assemble(geo, 2, **PROBLEMS["variable"]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
+
+
+def test_element_with_more_than_32_faces_is_rejected(rb):
+    geo = rb.DGFEMGeometry(_fan_mesh(rb, 40))
+    dg = rb.DGFEM(geo, polynomial_degree=1)
+    dg.add_data(**PROBLEMS["adr"]["data"])
+    with pytest.raises(rb.ReynaB200Error):
+        dg.dgfem(solve=False)

@@ -188,14 +188,18 @@ typedef struct {
     int32_t max_iter;
     double  rtol;              /* on ||r||_2 / ||b||_2 (preconditioned recurrence, verified on the true one) */
     int32_t check_every;       /* iterations between host convergence checks                                 */
+    double  accept_rtol;       /* a TRUE residual that stops improving at or below this is the rounding floor: the solve
+                                  ends there as converged (the floor spsolve has too); above it the iteration restarts
+                                  twice from the true residual before giving up.  <= 0: 1e-7                       */
 } rb_solve_opts;
 
 typedef struct {
     int32_t iterations;
     double  rel_residual;      /* true residual ||b - A x|| / ||b|| at exit                                   */
-    int32_t converged;         /* true residual <= rtol                                                      */
+    int32_t converged;         /* true residual <= rtol, or rounding floor reached at <= accept_rtol          */
     int32_t restarts;          /* restarts from the true residual after the recurrence residual converged     */
-    int32_t stagnated;         /* a restart no longer reduced the true residual: rounding floor reached       */
+    int32_t stagnated;         /* the true residual no longer improves (floor, or a plateau when !converged)  */
+    int32_t singular_blocks;   /* singular d x d diagonal blocks the block-Jacobi set-up replaced by identity */
 } rb_solve_info;
 
 typedef int (*rb_halo_fn)(void *user, double *x_dev, void *stream);          /* refresh ghosts of x            */

@@ -69,12 +69,13 @@ class RbMgDist(C.Structure):
 
 
 class RbSolveOpts(C.Structure):
-    _fields_ = [("method", C.c_int32), ("max_iter", C.c_int32), ("rtol", C.c_double), ("check_every", C.c_int32)]
+    _fields_ = [("method", C.c_int32), ("max_iter", C.c_int32), ("rtol", C.c_double), ("check_every", C.c_int32),
+                ("accept_rtol", C.c_double)]
 
 
 class RbSolveInfo(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("rel_residual", C.c_double), ("converged", C.c_int32),
-                ("restarts", C.c_int32), ("stagnated", C.c_int32)]
+                ("restarts", C.c_int32), ("stagnated", C.c_int32), ("singular_blocks", C.c_int32)]
 
 
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)

@@ -510,6 +510,7 @@ extern "C" int reyna_b200_csr_pattern(const rb_geom* g, const rb_structure* s, i
                                       int32_t* indices, void* stream) {
     RB_REQUIRE(g && s && indptr && indices, RB_E_ARG, "reyna_b200_csr_pattern: null argument");
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_csr_pattern: polynomial degree must be 1..3");
+    RB_REQUIRE(s->max_items <= rb::kMaxNb, RB_E_ARG, "reyna_b200_csr_pattern: an element has more than 64 contributing interior faces");
     const int d = (p + 1) * (p + 2) / 2;
     const int blocks = grid_for((g->n_rows + 31) / 32, kPatWarps, kNumSMs * kPatBlocksPerSM);
     return launch_pattern<false>(g, s, p, d, blocks, indptr, indices, (cudaStream_t)stream);
@@ -519,6 +520,7 @@ extern "C" int reyna_b200_csr_pattern_local(const rb_geom* g, const rb_structure
                                             int32_t* indices, void* stream) {
     RB_REQUIRE(g && s && indptr && indices, RB_E_ARG, "reyna_b200_csr_pattern_local: null argument");
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_csr_pattern_local: polynomial degree must be 1..3");
+    RB_REQUIRE(s->max_items <= rb::kMaxNb, RB_E_ARG, "reyna_b200_csr_pattern_local: an element has more than 64 contributing interior faces");
     const int d = (p + 1) * (p + 2) / 2;
     const int blocks = grid_for((g->n_rows + 31) / 32, kPatWarps, kNumSMs * kPatBlocksPerSM);
     return launch_pattern<true>(g, s, p, d, blocks, indptr, indices, (cudaStream_t)stream);

@@ -69,7 +69,9 @@ class DGFEM:
         # 'preconditioner': 'auto' = multigrid ('mg') when diffusion is present, block Jacobi ('bj') otherwise
         # 'mg_hierarchy': 'agglomerated' (P1 spaces on groups of 4 elements; defaults mg_nu 2, mg_omega 0.8, mg_alpha 2.2) or
         # 'aggregation' (piecewise constants; defaults 3, 0.7, 1.8) -- set 'mg_nu' / 'mg_omega' / 'mg_alpha' to override
-        self.solver_options = {'method': 'auto', 'rtol': 1e-14, 'max_iter': 200000, 'check_every': 10,
+        # 'rtol' is below the rounding floor on purpose: like spsolve, the iteration runs until the TRUE residual stops improving;
+        # at or below 'accept_rtol' that floor counts as convergence, above it the solve warns (solve_info['converged'] False)
+        self.solver_options = {'method': 'auto', 'rtol': 1e-14, 'accept_rtol': 1e-7, 'max_iter': 200000, 'check_every': 10,
                                'preconditioner': 'auto', 'mg_hierarchy': 'agglomerated'}
         self.solve_info: typing.Optional[dict] = None
         self.timings: dict = {}
@@ -589,7 +591,8 @@ class DGFEM:
         if method == 'auto':
             method = 'cg' if self.advection is None else 'bicgstab'
         opts = _lib.RbSolveOpts(method=0 if method == 'cg' else 1, max_iter=int(so.get('max_iter', 200000)),
-                                rtol=float(so.get('rtol', 1e-14)), check_every=int(so.get('check_every', 10)))
+                                rtol=float(so.get('rtol', 1e-14)), check_every=int(so.get('check_every', 10)),
+                                accept_rtol=float(so.get('accept_rtol', 1e-7)))
         prec = so.get('preconditioner', 'auto')
         if prec == 'auto':
             prec = 'mg' if self.diffusion is not None else 'bj'
@@ -601,8 +604,9 @@ class DGFEM:
         with torch.cuda.device(dev):
             # a side stream: the library replays the multigrid application as a CUDA graph, which the legacy default
             # stream cannot capture
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
+            caller = torch.cuda.current_stream()
+            side = self._stream(torch, dev, 'solve')
+            side.wait_stream(caller)
             torch.cuda.set_stream(side)
             sp = C.c_void_p(side.cuda_stream)
             try:
@@ -630,17 +634,21 @@ class DGFEM:
                 side.synchronize()
                 sol = x.cpu().numpy()
             finally:
-                torch.cuda.set_stream(torch.cuda.default_stream(dev))
+                torch.cuda.set_stream(caller)      # the caller's stream context is left as it was found
                 if mg.value:
                     L.reyna_b200_mg_destroy(mg)
         self.solve_info = dict(method=method, iterations=int(info.iterations), rel_residual=float(info.rel_residual),
                                converged=bool(info.converged), restarts=int(info.restarts),
                                preconditioner=prec, mg_levels=mg_levels, setup_seconds=setup_s,
-                               stagnated=bool(info.stagnated), seconds=time.perf_counter() - t0)
+                               stagnated=bool(info.stagnated), singular_blocks=int(info.singular_blocks),
+                               seconds=time.perf_counter() - t0)
         self.timings['solve_s'] = self.solve_info['seconds']
-        if not info.converged and not info.stagnated:
+        if not info.converged:
             warnings.warn(f"Krylov solver stopped after {info.iterations} iterations with relative residual "
-                          f"{info.rel_residual:.3e}")
+                          f"{info.rel_residual:.3e} (accepted: {float(so.get('accept_rtol', 1e-7)):.1e}); the solution may be "
+                          f"inaccurate")
+        if info.singular_blocks:
+            warnings.warn(f"{info.singular_blocks} singular diagonal blocks were replaced by identity in the preconditioner")
         return sol
 
     # ------------------------------------------------------------------------------------------------------------

@@ -77,6 +77,10 @@ class DistributedDGFEM:
         self.world = dist.get_world_size() if world is None else world
         self.global_geometry = geometry
         self.bounds = partition_bounds(int(geometry.n_elements), self.world)
+        if np.any(np.diff(self.bounds) <= 0):
+            # a rank without elements would skip the collectives of the Krylov solve and hang the others
+            raise ValueError(f'{int(geometry.n_elements)} elements cannot be split over {self.world} ranks '
+                             f'(ranges start at multiples of 4): use fewer ranks')
         self.part = partition_geometry(geometry, int(self.bounds[self.rank]), int(self.bounds[self.rank + 1]))
         self.plan = HaloPlan(geometry, self.bounds, self.rank)
         self.dg = DGFEM(self.part, polynomial_degree)
@@ -155,7 +159,8 @@ class DistributedDGFEM:
         if prec == "auto":
             prec = "mg" if dg.diffusion is not None else "bj"
         opts = _lib.RbSolveOpts(method=0 if method == "cg" else 1, max_iter=int(so.get("max_iter", 200000)),
-                                rtol=float(so.get("rtol", 1e-14)), check_every=int(so.get("check_every", 10)))
+                                rtol=float(so.get("rtol", 1e-14)), check_every=int(so.get("check_every", 10)),
+                                accept_rtol=float(so.get("accept_rtol", 1e-7)))
         info = _lib.RbSolveInfo()
         t0 = time.perf_counter()
         with torch.cuda.device(dev):
@@ -214,7 +219,12 @@ class DistributedDGFEM:
                                rel_residual=float(info.rel_residual), converged=bool(info.converged),
                                restarts=int(info.restarts), stagnated=bool(info.stagnated), world=self.world,
                                halo_exchanges=int(ex.value), allreduces=int(ar.value), n_ghost_elements=fg.n_elem - fg.n_rows,
+                               singular_blocks=int(info.singular_blocks),
                                context_seconds=t_ctx, setup_seconds=t_setup, seconds=time.perf_counter() - t0)
+        if not info.converged:
+            import warnings
+            warnings.warn(f"Krylov solver stopped after {info.iterations} iterations with relative residual "
+                          f"{info.rel_residual:.3e}; the solution may be inaccurate")
         return sol
 
     def _global_p0(self, torch, dev, dv):

@@ -174,3 +174,21 @@ def test_solution_matches_spsolve_at_config3a(rb):
                           diffusion=pr["data"]["diffusion"], reaction=pr["data"]["reaction"])
     for a, b in zip(e, eo):
         assert abs(a - b) <= util.TOL_ERRORS * abs(b)
+
+
+def test_default_solve_converges_at_the_rounding_floor_and_warns_otherwise(rb):
+    """Default options run to the rounding floor of the true residual and report it as converged; a solve that is cut short
+    above the acceptance tolerance warns instead of returning silently (the reference's spsolve is exact)."""
+    import warnings
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(4096, tiles=4, seed=9), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=2)
+    dg.add_data(**PROBLEMS["adr"]["data"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        dg.dgfem(solve=True)
+    si = dg.solve_info
+    assert si["converged"] and si["rel_residual"] <= 1e-7 and si["singular_blocks"] == 0, si
+    dg.solver_options.update(max_iter=5)
+    with pytest.warns(UserWarning, match="may be inaccurate"):
+        dg.dgfem(solve=True)
+    assert not dg.solve_info["converged"]

@@ -127,6 +127,12 @@ size_t reyna_b200_structure_workspace(int32_t n_rows, int32_t n_iface);
 int reyna_b200_structure(const rb_geom *g, int has_diffusion, const uint8_t *if_upwind, rb_structure *s,
                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same device work WITHOUT the synchronisation: for repeated assemblies on one geometry.  The four host counters of *s
+ * must hold the values an earlier reyna_b200_structure() call returned for the same (geometry, has_diffusion, if_upwind)
+ * -- with diffusion the structure does not depend on the coefficients at all. */
+int reyna_b200_structure_known(const rb_geom *g, int has_diffusion, const uint8_t *if_upwind, rb_structure *s,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 /* CSR index arrays of the structural pattern: indptr [n_rows*d+1], indices [nnz] (nnz = d*d*(n_rows+n_groups)). */
 int reyna_b200_csr_pattern(const rb_geom *g, const rb_structure *s, int p, int32_t *indptr, int32_t *indices,
                            void *stream);

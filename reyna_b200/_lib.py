@@ -16,7 +16,7 @@ RB_MAX_QV = 16
 RB_MAX_QE = 4
 
 EXPORTS = (
-    "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_csr_pattern", "reyna_b200_csr_pattern_local",
+    "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_structure_known", "reyna_b200_csr_pattern", "reyna_b200_csr_pattern_local",
     "reyna_b200_nccl_unique_id", "reyna_b200_comm_create", "reyna_b200_comm_destroy", "reyna_b200_dist_create", "reyna_b200_dist_destroy", "reyna_b200_dist_counters",
     "reyna_b200_nccl_halo", "reyna_b200_nccl_allreduce",
     "reyna_b200_assemble_workspace", "reyna_b200_assemble", "reyna_b200_assemble_prepare", "reyna_b200_assemble_range",
@@ -115,6 +115,8 @@ def lib() -> C.CDLL:
     L.reyna_b200_structure_workspace.argtypes = [i32, i32]
     L.reyna_b200_structure.restype = C.c_int
     L.reyna_b200_structure.argtypes = [C.POINTER(RbGeom), C.c_int, vp, C.POINTER(RbStructure), vp, C.c_size_t, vp]
+    L.reyna_b200_structure_known.restype = C.c_int
+    L.reyna_b200_structure_known.argtypes = [C.POINTER(RbGeom), C.c_int, vp, C.POINTER(RbStructure), vp, C.c_size_t, vp]
     L.reyna_b200_csr_pattern.restype = C.c_int
     L.reyna_b200_csr_pattern.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.c_int, vp, vp, vp]
     L.reyna_b200_csr_pattern_local.restype = C.c_int

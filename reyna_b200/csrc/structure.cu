@@ -247,8 +247,8 @@ extern "C" size_t reyna_b200_structure_workspace(int32_t n_rows, int32_t n_iface
     return sizeof(int32_t) * (2 * ((size_t)n_rows + 1) + scan_scratch_ints((int64_t)n_rows + 1) + 16);
 }
 
-extern "C" int reyna_b200_structure(const rb_geom* g, int has_diffusion, const uint8_t* if_upwind, rb_structure* s,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+static int structure_impl(const rb_geom* g, int has_diffusion, const uint8_t* if_upwind, rb_structure* s, void* workspace,
+                          size_t workspace_bytes, bool read_counters, void* stream) {
     RB_REQUIRE(g && s && workspace, RB_E_ARG, "reyna_b200_structure: null argument");
     RB_REQUIRE(has_diffusion || if_upwind, RB_E_NOCOEF,
                "reyna_b200_structure: no diffusion and no upwind flags (advection missing)");
@@ -283,6 +283,7 @@ extern "C" int reyna_b200_structure(const rb_geom* g, int has_diffusion, const u
     }
     rc = exclusive_scan_i32(grp_cnt, s->grp_off, (int64_t)n + 1, scratch, s->counts + 1, st);
     if (rc) return rc;
+    if (!read_counters) return 0;
     int32_t h[4];
     RB_CUDA(cudaMemcpyAsync(h, s->counts, sizeof(h), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
@@ -291,6 +292,17 @@ extern "C" int reyna_b200_structure(const rb_geom* g, int has_diffusion, const u
     s->n_dup_items = h[2];
     s->max_items = h[3];
     return 0;
+}
+
+extern "C" int reyna_b200_structure(const rb_geom* g, int has_diffusion, const uint8_t* if_upwind, rb_structure* s,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    return structure_impl(g, has_diffusion, if_upwind, s, workspace, workspace_bytes, true, stream);
+}
+
+extern "C" int reyna_b200_structure_known(const rb_geom* g, int has_diffusion, const uint8_t* if_upwind, rb_structure* s,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+    RB_REQUIRE(s && s->n_items >= 0 && s->n_groups >= 0, RB_E_ARG, "reyna_b200_structure_known: the host counters must be filled in");
+    return structure_impl(g, has_diffusion, if_upwind, s, workspace, workspace_bytes, false, stream);
 }
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -61,6 +61,9 @@ class DGFEM:
         self._B = None
         self._L = None
         self._dev = None           # device-resident system of the last dgfem() call
+        self._geo = geometry       # geometry the device path works on: `geometry`, or its locality renumbering (solve=True)
+        self._perm = None          # element permutation (new -> old) of `_geo`, None = identity
+        self.renumber = 'auto'     # 'auto': solve on a Morton renumbering when the element numbering has no locality; False: never
 
         self.element_reference_quadrature = None
         self.edge_reference_quadrature = None
@@ -154,7 +157,15 @@ class DGFEM:
             indices = dv['indices'].cpu().numpy()
             data = dv['data'].cpu().numpy()
             load = dv['load'].cpu().numpy()
-        self._B = csr_matrix((data, indices, indptr), shape=(N, dv.get('n_cols', N)))
+        B = csr_matrix((data, indices, indptr), shape=(N, dv.get('n_cols', N)))
+        if self._perm is not None:
+            # assembled in the locality renumbering (solve=True on a geometry without locality): back to the caller's numbering
+            d = self.dim_elem
+            dof = (np.asarray(self._geo.new_of_old, dtype=np.int64)[:, None] * d + np.arange(d)).reshape(-1)
+            B = B[dof][:, dof].tocsr()
+            B.sort_indices()
+            load = load[dof]
+        self._B = B
         self._L = csr_matrix(load.reshape(-1, 1))       # zero rows pruned, as main.py:218/225 leave it
         self.timings['d2h_s'] = time.perf_counter() - t0
 
@@ -171,12 +182,36 @@ class DGFEM:
 
         _time = time.time()
         self._B = self._L = None
+        # The multigrid hierarchy aggregates consecutive elements and the Krylov kernels gather neighbours: both need an
+        # element numbering with spatial locality.  The reference numbers elements in random seed order
+        # (polymesher/two_dimensional/main.py:111-165): such a geometry is solved on its Morton renumbering and the solution
+        # is handed back in the caller's numbering (B and L too, lazily).  Assembly alone (solve=False) keeps the numbering.
+        self._geo, self._perm = self.geometry, None
+        if solve and self.renumber and not hasattr(self.geometry, 'elem_gid') and \
+                getattr(flat_geometry(self.geometry), 'elem_gid', None) is None:
+            from .partition import locality_order, RenumberedGeometry
+            perm = locality_order(self.geometry)
+            if perm is not None:
+                work = getattr(self.geometry, '_rb_renumbered', None)
+                if work is None:
+                    work = RenumberedGeometry(self.geometry, perm)
+                    try:
+                        self.geometry._rb_renumbered = work
+                    except Exception:   # pragma: no cover
+                        pass
+                self._geo, self._perm = work, work.old_of_new
         self._assemble_device()
         if verbose == 1:
             print(f"Assembly: {time.time() - _time}")
 
         if solve:
-            self.solution = self._solve_device()
+            sol = self._solve_device()
+            if self._perm is not None:      # rows of the work numbering -> the caller's element numbering
+                d = self.dim_elem
+                out = np.empty_like(sol)
+                out.reshape(-1, d)[self._perm] = sol.reshape(-1, d)
+                sol = out
+            self.solution = sol
 
     # -- host: coefficient sampling -----------------------------------------------------------------------------------
     def _staging(self, torch, key, shape, dtype=None):
@@ -293,11 +328,11 @@ class DGFEM:
 
     # -- device ---------------------------------------------------------------------------------------------------------
     def _device_geometry(self, torch, dev, fg):
-        cache = getattr(self.geometry, '_rb_dev', None)
+        cache = getattr(fg, '_rb_dev', None)      # cached on the flat geometry (itself cached on its geometry object)
         if cache is None:
             cache = {}
             try:
-                self.geometry._rb_dev = cache
+                fg._rb_dev = cache
             except Exception:   # pragma: no cover
                 pass
         key = str(dev)
@@ -338,7 +373,7 @@ class DGFEM:
             raise _lib.ReynaB200Error(f'polynomial degree {p} is outside the supported range 1..3')
         tm = self.timings = {}
         t0 = time.perf_counter()
-        fg = flat_geometry(self.geometry)
+        fg = flat_geometry(self._geo)
         self._host = None
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream()
@@ -348,7 +383,7 @@ class DGFEM:
             tm['geometry_upload_s'] = time.perf_counter() - t0
 
             t1 = time.perf_counter()
-            pts = sampling.cached_points(self.geometry, fg, self.element_reference_quadrature, self.edge_reference_quadrature)
+            pts = sampling.cached_points(self._geo, fg, self.element_reference_quadrature, self.edge_reference_quadrature)
             cd, nbytes = self._sample_face_coefficients(torch, dev, fg, pts)
             flags, bnd_elem, bnd_off, bnd_face = self._boundary_lists(fg)
             bd = {k: torch.from_numpy(v).to(dev) for k, v in
@@ -425,8 +460,22 @@ class DGFEM:
                                                                     _ptr(counts))
         ws_bytes = L.reyna_b200_structure_workspace(R, fg.n_iface)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(L.reyna_b200_structure(C.byref(g), int(has_diff), _ptr(cd.get('if_upwind')), C.byref(st), _ptr(ws),
-                                          ws_bytes, sp), 'reyna_b200_structure')
+        # with diffusion the structure depends on the geometry only: after the first assembly on a geometry its four counters
+        # are known on the host and the call does not have to synchronise to return them
+        known = getattr(self._geo, '_rb_counts', None) if has_diff else None
+        key = (R, int(fg.n_iface))
+        if known is not None and known[0] == key:
+            st.n_items, st.n_groups, st.n_dup_items, st.max_items = known[1]
+            _lib.check(L.reyna_b200_structure_known(C.byref(g), 1, None, C.byref(st), _ptr(ws), ws_bytes, sp),
+                       'reyna_b200_structure_known')
+        else:
+            _lib.check(L.reyna_b200_structure(C.byref(g), int(has_diff), _ptr(cd.get('if_upwind')), C.byref(st), _ptr(ws),
+                                              ws_bytes, sp), 'reyna_b200_structure')
+            if has_diff:
+                try:
+                    self._geo._rb_counts = (key, (st.n_items, st.n_groups, st.n_dup_items, st.max_items))
+                except Exception:   # pragma: no cover - exotic geometry objects
+                    pass
         nnz = d * d * (R + st.n_groups)
         if nnz >= 2 ** 31:
             raise _lib.ReynaB200Error(f'nnz = {nnz} does not fit the int32 CSR indices')
@@ -476,8 +525,9 @@ class DGFEM:
                                                  ctx['spill'].data_ptr() + 8 * i0, _ptr(ctx['zero_count']), sp),
                            'reyna_b200_boundary')
 
-    def _finish_on_device(self, torch, L, dev, sp, fg, gd, ctx, bd, tm):
-        """The reference's B[0,0] quirk, join of the pattern stream, exact-zero pruning; returns the device-resident system."""
+    def _finish_on_device(self, torch, L, dev, sp, fg, gd, ctx, bd, tm, resolve=True):
+        """The reference's B[0,0] quirk, join of the pattern stream, exact-zero pruning; returns the device-resident system.
+        ``resolve=False`` leaves the count of exact zeros on the device (no host synchronisation; ``_resolve_zeros`` later)."""
         p, d, R, N, nnz = self.polydegree, ctx['d'], ctx['R'], ctx['N'], ctx['nnz']
         indptr, indices, data, load, zero_count = ctx['indptr'], ctx['indices'], ctx['data'], ctx['load'], ctx['zero_count']
         i32 = dict(dtype=torch.int32, device=dev)
@@ -492,8 +542,14 @@ class DGFEM:
         ctx['main'].wait_stream(ctx['side'])
         blocked = True
         structural = (indptr, indices, data)        # the solver (and its multigrid hierarchy) works on the block pattern
-        nz = int(zero_count.item())         # synchronises
         tm['structural_nnz'] = int(nnz)
+        if not resolve:
+            return dict(indptr=indptr, indices=indices, data=data, load=load, blocked=True, n=N, d=d, structural=structural,
+                        bbox=gd['bbox'], n_cols=int(getattr(self._geo, 'n_global_elements', R)) * d,
+                        structure=ctx['structure'], zero_count=zero_count, unresolved=True,
+                        _assemble_call=(ctx['g'], ctx['st'], ctx['co'], ctx['q'], data, load, zero_count, ctx['aws'],
+                                        ctx['aws_bytes']))
+        nz = int(zero_count.item())         # synchronises
         tm['exact_zeros'] = nz
         if nz > 0:
             # scipy's `+`/`-` drop exact zeros (main.py:211-225): compact to the reference's pattern
@@ -513,19 +569,20 @@ class DGFEM:
         tm['nnz'] = int(nnz)
         return dict(indptr=indptr, indices=indices, data=data, load=load, blocked=blocked, n=N, d=d, structural=structural,
                     bbox=gd['bbox'],
-                    n_cols=int(getattr(self.geometry, 'n_global_elements', R)) * d,
+                    n_cols=int(getattr(self._geo, 'n_global_elements', R)) * d,
                     structure=ctx['structure'],
                     # ctypes argument blocks of the assembly launch (bench.py re-launches it alone for the roofline)
                     _assemble_call=(ctx['g'], ctx['st'], ctx['co'], ctx['q'], structural[2], load, zero_count, ctx['aws'],
                                     ctx['aws_bytes']))
 
-    def _assemble_on_device(self, torch, L, dev, sp, fg, gd, cd, bd, tm):
+    def _assemble_on_device(self, torch, L, dev, sp, fg, gd, cd, bd, tm, resolve=True):
         """Everything from the uploaded samples to the device-resident CSR system in one go (inputs already resident in HBM:
-        bench.py's kernel-only timing, tools)."""
+        bench.py's kernel-only timing, tools).  With ``resolve=False`` the step ends without reading the exact-zero counter
+        back (every kernel has run; the caller checks ``int(dv['zero_count'])`` when it consumes the result)."""
         ctx = self._begin_on_device(torch, L, dev, sp, fg, gd, cd, tm)
         vs = sampling.volume_stream_of(fg)
         self._assemble_chunk(torch, L, sp, ctx, bd, 0, ctx['R'], 0, vs.n_rounds)
-        return self._finish_on_device(torch, L, dev, sp, fg, gd, ctx, bd, tm)
+        return self._finish_on_device(torch, L, dev, sp, fg, gd, ctx, bd, tm, resolve=resolve)
 
     # -- pipelined download of the result (``download_result``) ------------------------------------------------------------------
     def _start_index_download(self, torch, ctx) -> None:

@@ -75,6 +75,12 @@ class DistributedDGFEM:
         import torch.distributed as dist
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
+        # contiguous index ranges are compact patches only when the numbering has locality: a geometry in the reference's random
+        # seed order is partitioned (and solved) in its Morton renumbering; gather_solution() hands the caller's numbering back
+        from .partition import locality_order, RenumberedGeometry
+        self._perm = locality_order(geometry)
+        if self._perm is not None:
+            geometry = RenumberedGeometry(geometry, self._perm)
         self.global_geometry = geometry
         self.bounds = partition_bounds(int(geometry.n_elements), self.world)
         if np.any(np.diff(self.bounds) <= 0):
@@ -372,7 +378,12 @@ class DistributedDGFEM:
         mine = torch.from_numpy(np.ascontiguousarray(self.solution)).to(dev)
         outs = [torch.empty(s, dtype=torch.float64, device=dev) for s in sizes]
         dist.all_gather(outs, mine) if len(set(sizes)) == 1 else self._all_gather_uneven(dist, outs, mine)
-        return torch.cat(outs).cpu().numpy()
+        sol = torch.cat(outs).cpu().numpy()
+        if self._perm is not None:
+            out = np.empty_like(sol)
+            out.reshape(-1, d)[self._perm] = sol.reshape(-1, d)
+            sol = out
+        return sol
 
     def _all_gather_uneven(self, dist, outs, mine):
         for r in range(self.world):

@@ -30,9 +30,79 @@ def partition_bounds(n_elements: int, world: int) -> np.ndarray:
 
 
 def morton_partition_order(geometry) -> np.ndarray:
-    """Permutation that numbers elements along a Z-order curve of their seed points (for meshes without locality)."""
+    """Permutation (new -> old) that numbers elements along a Z-order curve of their bounding-box centres: the order in which
+    contiguous index ranges are compact patches (partitions with short halos, multigrid aggregates of neighbouring
+    elements).  The reference's mesher numbers elements in random seed order (polymesher/two_dimensional/main.py:111-165)."""
     from .mesh import morton_order
-    return morton_order(np.asarray(geometry.mesh.filtered_points, dtype=float))
+    bb = flat_geometry(geometry).bbox
+    return morton_order(np.column_stack((0.5 * (bb[:, 0] + bb[:, 1]), 0.5 * (bb[:, 2] + bb[:, 3]))))
+
+
+def locality_order(geometry, factor: float = 8.0) -> typing.Optional[np.ndarray]:
+    """``None`` when the element numbering already has spatial locality (mean index distance of face neighbours at most
+    ``factor * sqrt(E)``: row-major, Morton, Hilbert ... numberings), otherwise ``morton_partition_order(geometry)``.
+    Cached on the geometry object."""
+    cached = getattr(geometry, '_rb_locality', None)
+    if cached is not None:
+        return cached[0]
+    fg = flat_geometry(geometry)
+    perm = None
+    if fg.n_iface > 0 and fg.n_elem >= 64:
+        gap = float(np.abs(fg.ielem[:, 0].astype(np.int64) - fg.ielem[:, 1].astype(np.int64)).mean())
+        if gap > factor * np.sqrt(fg.n_elem):
+            perm = morton_partition_order(geometry)
+    try:
+        geometry._rb_locality = (perm,)
+    except Exception:   # pragma: no cover - exotic geometry objects
+        pass
+    return perm
+
+
+class RenumberedGeometry:
+    """The same geometry with elements renumbered by ``perm`` (new -> old); faces, nodes and boundary edges keep their
+    numbering.  Carries the attribute names ``DGFEM`` / ``BoundaryInformation`` read; ``old_of_new`` / ``new_of_old`` map
+    element ids."""
+
+    def __init__(self, parent, perm: np.ndarray):
+        fg = flat_geometry(parent)
+        E = fg.n_elem
+        perm = np.asarray(perm, dtype=np.int64)
+        if perm.shape != (E,) or not np.array_equal(np.sort(perm), np.arange(E)):
+            raise ValueError('perm must be a permutation of the elements')
+        inv = np.empty(E, dtype=np.int64)
+        inv[perm] = np.arange(E)
+        self.parent, self.old_of_new, self.new_of_old = parent, perm, inv
+
+        def ragged(off, idx):
+            cnt = np.diff(off.astype(np.int64))[perm]
+            new_off = np.zeros(E + 1, dtype=np.int64)
+            np.cumsum(cnt, out=new_off[1:])
+            src = np.repeat(off[:-1].astype(np.int64)[perm] - new_off[:-1], cnt) + np.arange(int(new_off[-1]), dtype=np.int64)
+            return new_off, idx[src], cnt
+
+        tri_off, tri_sel, tcnt = ragged(fg.tri_off, np.arange(fg.n_tri, dtype=np.int64))
+        poly_off, poly_vtx, _ = ragged(fg.poly_off, fg.poly_vtx)
+        f = types.SimpleNamespace(
+            n_nodes=fg.n_nodes, n_elem=E, n_tri=fg.n_tri, n_iface=fg.n_iface, n_bface=fg.n_bface, nodes=fg.nodes,
+            tri=np.ascontiguousarray(fg.tri[tri_sel]), tri_elem=np.repeat(np.arange(E, dtype=np.int32), tcnt),
+            tri_off=tri_off.astype(np.int32), bbox=np.ascontiguousarray(fg.bbox[perm]), area=np.ascontiguousarray(fg.area[perm]),
+            poly_off=poly_off.astype(np.int32), poly_vtx=np.ascontiguousarray(poly_vtx),
+            iedge=fg.iedge, ielem=np.ascontiguousarray(inv[fg.ielem.astype(np.int64)].astype(np.int32)), inorm=fg.inorm,
+            bedge=fg.bedge, belem=inv[fg.belem.astype(np.int64)].astype(np.int32), bnorm=fg.bnorm,
+        )
+        self._rb_flat = f
+        self.nodes = fg.nodes
+        self.n_elements = E
+        self.h = parent.h
+        self.boundary_edges = f.bedge
+        self.boundary_edges_to_element = f.belem
+        self.boundary_normals = f.bnorm
+        self.interior_edges = f.iedge
+        self.interior_edges_to_element = f.ielem
+        self.interior_normals = f.inorm
+        self.elem_bounding_boxes = f.bbox
+        self.areas = f.area
+        self.mesh = getattr(parent, "mesh", None)
 
 
 class PartitionedGeometry:

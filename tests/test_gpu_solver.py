@@ -192,3 +192,44 @@ def test_default_solve_converges_at_the_rounding_floor_and_warns_otherwise(rb):
     with pytest.warns(UserWarning, match="may be inaccurate"):
         dg.dgfem(solve=True)
     assert not dg.solve_info["converged"]
+
+
+def test_solver_is_independent_of_the_element_numbering(rb):
+    """The reference's mesher numbers elements in random seed order (polymesher/two_dimensional/main.py:111-165).  A shuffled
+    65k-element mesh is solved on its Morton renumbering: about the same iteration count as the ordered mesh, the solution
+    (in the caller's numbering) equal to the ordered one, and B / L in the caller's numbering too."""
+    from reyna_b200.partition import RenumberedGeometry, locality_order
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(65536, tiles=4, seed=3), subtriangulation="fan")
+    assert locality_order(geo) is None
+    ref = rb.DGFEM(geo, polynomial_degree=2)
+    ref.add_data(**PROBLEMS["adr"]["data"])
+    ref.dgfem(solve=True)
+    shuffle = np.random.default_rng(7).permutation(geo.n_elements)
+    sgeo = RenumberedGeometry(geo, shuffle)                       # new element i = old element shuffle[i]
+    assert locality_order(sgeo) is not None
+    dg = rb.DGFEM(sgeo, polynomial_degree=2)
+    dg.add_data(**PROBLEMS["adr"]["data"])
+    dg.dgfem(solve=True)
+    assert dg._perm is not None
+    assert dg.solve_info["converged"] and dg.solve_info["iterations"] <= 1.3 * ref.solve_info["iterations"] + 10, \
+        (dg.solve_info, ref.solve_info)
+    d = dg.dim_elem
+    mine = dg.solution.reshape(-1, d)                             # shuffled numbering
+    theirs = ref.solution.reshape(-1, d)[shuffle]
+    assert util.rel_l2(mine.reshape(-1), theirs.reshape(-1)) <= util.TOL_SOLUTION
+    # the matrix comes back in the caller's (shuffled) numbering: compare with a plain assembly in that numbering
+    asm = rb.DGFEM(sgeo, polynomial_degree=2)
+    asm.add_data(**PROBLEMS["adr"]["data"])
+    asm.dgfem(solve=False)
+    assert asm._perm is None
+    max_rel, bad, noise = util.compare_csr(dg.B, asm.B, d)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(asm.L.todense())) <= util.TOL_ENTRY
+    # without the renumbering the hierarchy aggregates unrelated elements
+    dg.renumber = False
+    dg.solver_options.update(max_iter=3 * ref.solve_info["iterations"])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dg.dgfem(solve=True)
+    assert not dg.solve_info["converged"] or dg.solve_info["iterations"] > 1.5 * ref.solve_info["iterations"]

@@ -124,12 +124,9 @@ class ClockSampler:
 # reference arm / cpu baseline: the oracle port on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
 def _oracle_worker(args):
-    path, p, problem = args
-    import reyna_b200 as rb
+    g, p, problem = args
     from oracle import dg_oracle
     from reyna_b200.problems import PROBLEMS
-    geo = rb.load_geometry_cache(path)
-    fg = dg_oracle.flatten_geometry(geo)
     co = dg_oracle.wrap_callables(**PROBLEMS[problem]["data"])
     # warm the numba-compiled callables (compile time is not part of the reference's assembly time either)
     x = np.zeros((4, 2))
@@ -137,28 +134,35 @@ def _oracle_worker(args):
         if f is not None:
             f(x)
     t0 = time.perf_counter()
-    B, L, info = dg_oracle.assemble(fg, p, precompiled=co)
-    return time.perf_counter() - t0, int(info.dim_system), int(B.nnz)
+    B, L, info = dg_oracle.assemble(g, p, precompiled=co, mirror_index_quirk=False)
+    d = info.dim_elem
+    rows = g.n_rows * d
+    return time.perf_counter() - t0, int(rows), int(B[:rows].nnz)
 
 
-def oracle_throughput(sample_elements: int, p: int, problem: str, procs: int, repeats: int = 1):
-    """Assembled DoF/s of the oracle port: `procs` concurrent processes, each assembling its own `sample_elements`
-    partition (the reference is a single-threaded Python program; independent partitions are the only way it scales)."""
+def oracle_throughput(n_elements: int, sample_elements: int, p: int, problem: str, procs: int, repeats: int = 1):
+    """Assembled DoF/s of the oracle port on REAL SLICES of the workload: `procs` concurrent processes, process k assembling
+    the block rows of `sample_elements` consecutive elements of the `n_elements` mesh (slices spread over the mesh; the
+    ghost-inclusive sub-mesh is cut with reyna_b200.partition.partition_geometry).  The reference is a single-threaded Python
+    program; independent row slices are the only way it scales.  Returns (DoF per step, step times, nnz per step)."""
     import multiprocessing as mp
-    _, path, _ = workload_geometry(sample_elements)
+    from oracle import dg_oracle
+    from reyna_b200.partition import partition_geometry
+    geo, _, _ = workload_geometry(n_elements)
+    sample_elements = min(sample_elements, n_elements)
+    starts = [((k * (n_elements - sample_elements)) // max(1, procs - 1)) // 4 * 4 if procs > 1 else 0 for k in range(procs)]
+    subs = [dg_oracle.flatten_partition(partition_geometry(geo, lo, lo + sample_elements)) for lo in starts]
     ctx = mp.get_context("spawn")
     times = []
-    ndof = 0
+    ndof = nnz = 0
     with ctx.Pool(procs) as pool:
         for _ in range(repeats):
-            t0 = time.perf_counter()
-            res = pool.map(_oracle_worker, [(path, p, problem)] * procs)
-            wall = time.perf_counter() - t0
+            res = pool.map(_oracle_worker, [(g, p, problem) for g in subs])
             ndof = sum(r[1] for r in res)
+            nnz = sum(r[2] for r in res)
             # per-step time = slowest worker (excludes process start-up / numba compilation, which dgfem() timing excludes too)
             times.append(max(r[0] for r in res))
-            del wall
-    return ndof, times
+    return ndof, times, nnz
 
 
 def host_cores() -> int:
@@ -173,18 +177,22 @@ def run_reference(args, rank: int) -> None:
         return
     cores = max(1, min(host_cores(), 32))
     sample = args.reference_sample
-    ndof, times = oracle_throughput(sample, args.degree, args.problem, cores, repeats=args.warmup + args.steps)
+    ndof, times, nnz = oracle_throughput(args.elements, sample, args.degree, args.problem, cores,
+                                         repeats=args.warmup + args.steps)
     timed = times[args.warmup:]
     t = float(np.mean(timed))
     value = ndof / t
+    d = (args.degree + 1) * (args.degree + 2) // 2
     sample_txt = (f"{cores} concurrent oracle processes (oracle/dg_oracle.py, numpy port of reyna's dgfem(solve=False)), each "
-                  f"assembling one {sample}-element partition of the workload per step")
+                  f"assembling the block rows of {sample} consecutive elements of the {args.elements}-element workload per step "
+                  f"({ndof} DoF, {nnz} non-zeros per step; slices spread over the mesh, ghost layer included)")
     line = {
         "impl": "reference", "metric": "assembled DoF/s", "value": value, "unit": "DoF/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.elements, args.degree, args.problem), "elements": args.elements,
-                   "degree": args.degree, "problem": args.problem},
+                   "degree": args.degree, "problem": args.problem, "dof": args.elements * d,
+                   "sampled_dof_per_step": ndof, "sampled_nnz_per_step": nnz},
         "cpu_baseline": {"value": value, "unit": "DoF/s", "cores": cores, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": "DoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -391,9 +399,23 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         wall = time.perf_counter() - ts
         pr = PROBLEMS[args.problem]
         l2 = None
-        if ddg is None and pr.get("exact") is not None:
+        if pr.get("exact") is not None:
             has_diff = pr["data"].get("diffusion") is not None
-            l2, dgn, h1 = dg.errors(pr["exact"], pr["grad_exact"] if has_diff else None)
+            if ddg is None:
+                l2, dgn, h1 = dg.errors(pr["exact"], pr["grad_exact"] if has_diff else None)
+            else:
+                # the gathered solution of the distributed solve, measured on rank 0 with the single-GPU error kernels
+                xg = ddg.gather_solution()
+                if rank == 0:
+                    chk = rb.DGFEM(geo, polynomial_degree=p)
+                    chk.device = dev
+                    chk.add_data(**pr["data"])
+                    chk.orders = None
+                    chk.dim_elem = d
+                    chk.dim_system = d * geo.n_elements
+                    chk.solution = xg
+                    l2, dgn, h1 = chk.errors(pr["exact"], pr["grad_exact"] if has_diff else None)
+                    del chk
         solve_line = {"dgfem_solve_true_wall_s": wall, "solve_s": si["seconds"], "setup_s": si["setup_seconds"],
                       "method": si["method"], "preconditioner": si["preconditioner"], "iterations": si["iterations"],
                       "true_rel_residual": si["rel_residual"], "stopped_at_rounding_floor": si["stagnated"],
@@ -434,11 +456,11 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         line["solve"] = solve_line
     if world == 1 and not args.no_cpu_baseline:
         cores = 1
-        ndof, times = oracle_throughput(args.baseline_sample, p, args.problem, cores, repeats=1)
+        ndof, times, _ = oracle_throughput(args.elements, args.baseline_sample, p, args.problem, cores, repeats=1)
         line["cpu_baseline"] = {
             "value": ndof / times[0], "unit": "DoF/s", "cores": cores, "kind": "port",
-            "sample": f"oracle/dg_oracle.py (numpy port of reyna's dgfem(solve=False)) assembling one "
-                      f"{args.baseline_sample}-element partition of the workload, {times[0]:.1f} s, 1 process"}
+            "sample": f"oracle/dg_oracle.py (numpy port of reyna's dgfem(solve=False)) assembling the block rows of the first "
+                      f"{min(args.baseline_sample, args.elements)} elements of the workload, {times[0]:.1f} s, 1 process"}
     emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
@@ -477,11 +499,24 @@ def main() -> None:
     ap.add_argument("--elements", type=int, default=1048576)
     ap.add_argument("--degree", type=int, default=2)
     ap.add_argument("--problem", default="adr")
+    ap.add_argument("--config", type=int, default=None, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configuration (sets --elements/--degree/--problem): 1 README 1024 p1 adr, 2 16k p1 "
+                         "diffusion, 3 65k p2 adr (use --degree 3 for 3b), 4 262k p2 hyperbolic, 5 1M p2 adr (default)")
     ap.add_argument("--baseline-sample", type=int, default=65536, help="elements of the cpu_baseline sample")
     ap.add_argument("--reference-sample", type=int, default=32768, help="elements per process and step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the dgfem(solve=True) wall-time measurement")
     args = ap.parse_args()
+    if args.config is not None:
+        preset = {1: (1024, 1, "adr"), 2: (16384, 1, "diffusion"), 3: (65536, 2, "adr"), 4: (262144, 2, "hyperbolic"),
+                  5: (1048576, 2, "adr")}[args.config]
+        explicit = {a.split("=")[0] for a in sys.argv[1:] if a.startswith("--")}
+        if "--elements" not in explicit:
+            args.elements = preset[0]
+        if "--degree" not in explicit:
+            args.degree = preset[1]
+        if "--problem" not in explicit:
+            args.problem = preset[2]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -83,6 +83,22 @@ def flatten_geometry(geometry) -> types.SimpleNamespace:
     return g
 
 
+def flatten_partition(part) -> types.SimpleNamespace:
+    """Oracle geometry of a ``reyna_b200.partition.PartitionedGeometry``: its owned elements [0, n_rows) followed by the ghost
+    elements across the cut faces, as a stand-alone mesh.  ``assemble`` on it yields, in block rows [0, n_rows), exactly the
+    rows of the global matrix (local column numbering; ghost rows are incomplete and must be ignored): the test-suite and
+    bench.py use it to check / time real slices of workloads that are too large for one oracle call."""
+    f = part._rb_flat
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    return types.SimpleNamespace(
+        nodes=np.ascontiguousarray(f.nodes, dtype=np.float64), n_elements=int(f.n_elem), n_rows=int(f.n_rows),
+        tri=i64(f.tri), tri_elem=i64(f.tri_elem), bbox=np.asarray(f.bbox, dtype=np.float64).reshape(-1, 4),
+        area=np.asarray(f.area, dtype=np.float64), poly_off=i64(f.poly_off), poly_vtx=i64(f.poly_vtx),
+        iedge=i64(f.iedge).reshape(-1, 2), ielem=i64(f.ielem).reshape(-1, 2),
+        inorm=np.asarray(f.inorm, dtype=np.float64).reshape(-1, 2), bedge=i64(f.bedge).reshape(-1, 2), belem=i64(f.belem),
+        bnorm=np.asarray(f.bnorm, dtype=np.float64).reshape(-1, 2), elem_gid=i64(f.elem_gid))
+
+
 # --------------------------------------------------------------------------------------------------------------
 # quadrature and basis
 # --------------------------------------------------------------------------------------------------------------

@@ -44,6 +44,7 @@ def test_golden_parity(rb, mesh, key):
     assert B.indices.dtype == np.int32 and B.indptr.dtype == np.int32
     assert B.has_canonical_format
     max_rel, bad, noise = util.compare_csr(B, Bref, dg.dim_elem)
+    util.note(f"[parity] golden {mesh} {key}: max block-relative error {max_rel:.2e}, noise-level pattern entries {noise}")
     assert bad == 0, f"{bad} pattern mismatches that are not rounding noise"
     assert max_rel <= util.TOL_ENTRY
     if noise == 0:
@@ -216,6 +217,7 @@ def test_scale_oracle_parity_65k_p2(rb, big):
     dg = _run(rb, big, "adr", 2, solve=False)
     B, L, info = dg_oracle.assemble(big, 2, **PROBLEMS["adr"]["data"])
     max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    util.note(f"[parity] 65536 elements adr p=2: max block-relative error {max_rel:.2e}, noise-level pattern entries {noise}")
     assert bad == 0 and max_rel <= util.TOL_ENTRY
     assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
 

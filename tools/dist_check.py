@@ -28,11 +28,15 @@ def main():
     sizes = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [65536]
     probs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["adr", "diffusion"]
     p = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    shuffle = len(sys.argv) > 4 and sys.argv[4] == "shuffle"      # element numbering without locality (the reference's meshes)
     for E in sizes:
         if rank == 0:
             workload_geometry(E)
         dist.barrier()
         geo, _, _ = workload_geometry(E)
+        if shuffle:
+            from reyna_b200.partition import RenumberedGeometry
+            geo = RenumberedGeometry(geo, np.random.default_rng(5).permutation(geo.n_elements))
         for name in probs:
             ddg = DistributedDGFEM(geo, p, device=dev)
             ddg.add_data(**PROBLEMS[name]["data"])
@@ -45,7 +49,7 @@ def main():
             dist.barrier()
             dt = time.perf_counter() - t0
             x = ddg.gather_solution()
-            out = dict(E=E, problem=name, p=p, world=world, solve_s=round(dt, 3), info=ddg.solve_info)
+            out = dict(E=E, problem=name, p=p, world=world, shuffled=bool(shuffle), solve_s=round(dt, 3), info=ddg.solve_info)
             if rank == 0 and E <= 262144:
                 dg = rb.DGFEM(geo, p)
                 dg.device = dev

@@ -197,6 +197,14 @@ typedef struct {
     double  accept_rtol;       /* a TRUE residual that stops improving at or below this is the rounding floor: the solve
                                   ends there as converged (the floor spsolve has too); above it the iteration restarts
                                   twice from the true residual before giving up.  <= 0: 1e-7                       */
+    /* Flow-ordered block Gauss-Seidel sweep (single GPU, BiCGStab, no multigrid): for advection-reaction WITHOUT diffusion
+     * the block rows only couple to their upwind neighbours, so in a topological order of the upwind graph B is block lower
+     * triangular and one sweep solves the system; with cycles in the flow the sweep is the preconditioner.  sweep_elems
+     * lists all elements level by level (level = 1 + max level of the upwind neighbours; elements on cycles last),
+     * sweep_level_off the first entry of every level.  sweep_levels == 0: block Jacobi / multigrid as before.        */
+    const int32_t *sweep_elems;      /* DEVICE [n / d]                                                              */
+    const int32_t *sweep_level_off;  /* HOST   [sweep_levels + 1]                                                   */
+    int32_t sweep_levels;
 } rb_solve_opts;
 
 typedef struct {

@@ -70,7 +70,8 @@ class RbMgDist(C.Structure):
 
 class RbSolveOpts(C.Structure):
     _fields_ = [("method", C.c_int32), ("max_iter", C.c_int32), ("rtol", C.c_double), ("check_every", C.c_int32),
-                ("accept_rtol", C.c_double)]
+                ("accept_rtol", C.c_double), ("sweep_elems", C.c_void_p), ("sweep_level_off", C.c_void_p),
+                ("sweep_levels", C.c_int32)]
 
 
 class RbSolveInfo(C.Structure):

@@ -281,6 +281,42 @@ __global__ void __launch_bounds__(kVecThreads) k_precond(int n, int d, const dou
         z[i] = precond_row(minv, s, (int)i, d);
 }
 
+// One level of the flow-ordered block Gauss-Seidel sweep (advection-reaction without diffusion: B is block lower triangular in
+// the topological order of the upwind graph, solver option sweep_*):  z_e = D_e^-1 (v_e - sum_{o != e} B_eo z_o) for the
+// elements of the level; the z_o of upwind neighbours were written by earlier levels (z is zeroed before the sweep, so a
+// neighbour that is not upwind -- a cycle of the flow -- contributes nothing).  G lanes per element, lane j < d owns row j.
+template <int G>
+__global__ void __launch_bounds__(128) k_sweep_level(int n_level, const int32_t* __restrict__ elems, int d,
+                                                     const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                     const double* __restrict__ data, const double* __restrict__ minv,
+                                                     const double* __restrict__ v, double* __restrict__ z) {
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int j = threadIdx.x % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
+    const bool on = gid < n_level;
+    const int e = on ? elems[gid] : 0;
+    double sj = 0.0;
+    if (on && j < d) {
+        const int row = e * d + j;
+        double acc = v[row];
+        const int lo = indptr[row], hi = indptr[row + 1];
+        const int c0 = e * d, c1 = c0 + d;
+        for (int k = lo; k < hi; ++k) {
+            const int c = indices[k];
+            if (c < c0 || c >= c1) acc = fma(-data[k], z[c], acc);
+        }
+        sj = acc;
+    }
+    // z_e = Minv_e s_e
+    double zj = 0.0;
+    const double* M = minv + (size_t)e * d * d;
+    for (int k = 0; k < d; ++k) {
+        const double sk = __shfl_sync(gmask, sj, (threadIdx.x % 32) / G * G + k);
+        if (on && j < d) zj = fma(M[j * d + k], sk, zj);
+    }
+    if (on && j < d) z[e * d + j] = zj;
+}
+
 __global__ void __launch_bounds__(kVecThreads) k_dot2(int n, const double* __restrict__ a, const double* __restrict__ b2,
                                                       double* __restrict__ partial) {
     // partial0 = (a,b2), partial1 = (a,a)
@@ -384,7 +420,28 @@ struct Solver {
     PrecGraph graphs[4];
     int n_graphs = 0;
 
+    // flow-ordered block Gauss-Seidel sweep (rb_solve_opts.sweep_*), or null
+    const int32_t* sweep_elems = nullptr;
+    const int32_t* sweep_off = nullptr;    // host
+    int sweep_levels = 0;
+
+    int sweep_launch(const double* v, double* z) {
+        RB_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * (size_t)n, st));
+        for (int l = 0; l < sweep_levels; ++l) {
+            const int cnt = sweep_off[l + 1] - sweep_off[l];
+            if (cnt <= 0) continue;
+            if (d <= 8)
+                k_sweep_level<8><<<(int)div_up((int64_t)cnt * 8, 128), 128, 0, st>>>(cnt, sweep_elems + sweep_off[l], d, indptr, indices,
+                                                                                    data, minv, v, z);
+            else
+                k_sweep_level<16><<<(int)div_up((int64_t)cnt * 16, 128), 128, 0, st>>>(cnt, sweep_elems + sweep_off[l], d, indptr,
+                                                                                      indices, data, minv, v, z);
+        }
+        RB_LAUNCH_CHECK("k_sweep_level");
+        return 0;
+    }
     int precond_launch(const double* v, double* z) {
+        if (sweep_levels > 0) return sweep_launch(v, z);
         k_precond<<<nb, kVecThreads, 0, st>>>(n, d, minv, v, z);
         RB_LAUNCH_CHECK("k_precond");
         if (mg) return mg_apply_add(mg, v, z, st);
@@ -392,7 +449,7 @@ struct Solver {
     }
     // z = M^-1 v: block Jacobi, plus the multigrid coarse-space correction when a hierarchy is attached
     int precond(const double* v, double* z) {
-        if (!use_graphs || !mg) return precond_launch(v, z);
+        if (!use_graphs || (!mg && sweep_levels == 0)) return precond_launch(v, z);
         for (int i = 0; i < n_graphs; ++i)
             if (graphs[i].v == v && graphs[i].z == z) {
                 RB_CUDA(cudaGraphLaunch(graphs[i].exec, st));
@@ -518,6 +575,13 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     }
     s.use_graphs = (halo == nullptr);
     RB_LAUNCH_CHECK("block_jacobi_setup");
+    if (opts->sweep_levels > 0 && opts->sweep_elems && opts->sweep_level_off && !halo && !mg && opts->method != 0) {
+        // advection-reaction without diffusion: B is block triangular along the flow -> one sweep is (nearly) the solve
+        s.sweep_elems = opts->sweep_elems;
+        s.sweep_off = opts->sweep_level_off;
+        s.sweep_levels = opts->sweep_levels;
+        if ((rc0 = s.sweep_launch(rhs, x))) return rc0;     // x0 = sweep(b): exact when the upwind graph has no cycle
+    }
 
     int rc;
     const bool cg = opts->method == 0;
@@ -598,6 +662,10 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
         if (!(true_rr == true_rr)) { set_error("Krylov iteration produced NaN"); break; }
         if (true_rr <= target2) { done = true; break; }
         if (stagnated) break;                      // floor verified inside the last run (true_rr is the final residual)
+        if (s.sweep_levels > 0 && prev_true_rr < 0.0 && true_rr <= 1e-24 * (bb > 0.0 ? bb : 1.0)) {
+            stagnated = true;                      // the flow sweep was a direct solve: x0 is at the rounding floor already
+            break;
+        }
         if (prev_true_rr >= 0.0 && true_rr > 0.25 * prev_true_rr) {
             if (true_rr <= accept2 || ++flat_restarts >= 2) { stagnated = true; break; }   // rounding floor / plateau
         } else {

@@ -69,7 +69,8 @@ class DGFEM:
         self.edge_reference_quadrature = None
 
         # Krylov replacement of spsolve (main.py:231)
-        # 'preconditioner': 'auto' = multigrid ('mg') when diffusion is present, block Jacobi ('bj') otherwise
+        # 'preconditioner': 'auto' = multigrid ('mg') when diffusion is present, otherwise the flow-ordered block Gauss-Seidel sweep
+        # ('sweep'; 'bj' = plain block Jacobi)
         # 'mg_hierarchy': 'agglomerated' (P1 spaces on groups of 4 elements; defaults mg_nu 2, mg_omega 0.8, mg_alpha 2.2) or
         # 'aggregation' (piecewise constants; defaults 3, 0.7, 1.8) -- set 'mg_nu' / 'mg_omega' / 'mg_alpha' to override
         # 'rtol' is below the rounding floor on purpose: like spsolve, the iteration runs until the TRUE residual stops improving;
@@ -238,6 +239,7 @@ class DGFEM:
     def _sample_face_coefficients(self, torch, dev, fg, pts):
         """Interior-face and boundary-face samples (q-major) + upwind flags: everything the structure and the prepass need."""
         dev_t, nbytes = {}, 0
+        self._upwind_host = None
         if fg.n_iface:
             mid, Xf = pts['mid_i'], pts['Xi']
             if self.diffusion is not None:
@@ -251,6 +253,7 @@ class DGFEM:
                 upw = ((b_mid[:, 0] * fg.inorm[:, 0] + b_mid[:, 1] * fg.inorm[:, 1]) >= 1e-12).astype(np.uint8)
                 dev_t['if_upwind'] = torch.from_numpy(upw).to(dev)
                 nbytes += upw.nbytes
+                self._upwind_host = upw
         if fg.n_bface:
             mid, Xb = pts['mid_b'], pts['Xb']
             nbytes += self._put(torch, dev, dev_t, 'bf_g', self.dirichlet_bcs, Xb, ())
@@ -652,12 +655,29 @@ class DGFEM:
                                 accept_rtol=float(so.get('accept_rtol', 1e-7)))
         prec = so.get('preconditioner', 'auto')
         if prec == 'auto':
-            prec = 'mg' if self.diffusion is not None else 'bj'
+            # diffusion: multigrid; advection-reaction only: the flow-ordered block Gauss-Seidel sweep (a direct solve when
+            # the upwind graph has no cycle)
+            prec = 'mg' if self.diffusion is not None else 'sweep'
+        if prec == 'sweep' and (self.diffusion is not None or method != 'bicgstab' or getattr(self, '_upwind_host', None) is None):
+            prec = 'bj'
         info = _lib.RbSolveInfo()
         t0 = time.perf_counter()
         s_indptr, s_indices, s_data = dv['structural']
         mg = C.c_void_p(None)
         mg_levels = None
+        sweep = None
+        if prec == 'sweep':
+            from .flow import flow_levels
+            fgw = flat_geometry(self._geo)
+            order, level_off, n_cyclic = flow_levels(fgw.ielem, self._upwind_host, N // d)
+            if n_cyclic and level_off.shape[0] - 1 > 8 * int(np.sqrt(N // d)) + 64:
+                prec = 'bj'        # closed streamlines and a nearly sequential order: the sweep would be all launch latency
+        if prec == 'sweep':
+            sweep = dict(order=torch.from_numpy(order).to(dev), off=np.ascontiguousarray(level_off, dtype=np.int32),
+                         levels=int(level_off.shape[0] - 1), cyclic=n_cyclic)
+            opts.sweep_elems = _ptr(sweep['order'])
+            opts.sweep_level_off = sweep['off'].ctypes.data
+            opts.sweep_levels = sweep['levels']
         with torch.cuda.device(dev):
             # a side stream: the library replays the multigrid application as a CUDA graph, which the legacy default
             # stream cannot capture
@@ -698,6 +718,8 @@ class DGFEM:
                                converged=bool(info.converged), restarts=int(info.restarts),
                                preconditioner=prec, mg_levels=mg_levels, setup_seconds=setup_s,
                                stagnated=bool(info.stagnated), singular_blocks=int(info.singular_blocks),
+                               sweep_levels=sweep['levels'] if sweep else None,
+                               flow_cycles_broken=sweep['cyclic'] if sweep else None,
                                seconds=time.perf_counter() - t0)
         self.timings['solve_s'] = self.solve_info['seconds']
         if not info.converged:

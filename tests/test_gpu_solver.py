@@ -233,3 +233,58 @@ def test_solver_is_independent_of_the_element_numbering(rb):
         warnings.simplefilter("ignore")
         dg.dgfem(solve=True)
     assert not dg.solve_info["converged"] or dg.solve_info["iterations"] > 1.5 * ref.solve_info["iterations"]
+
+
+def _rotating(x):
+    out = np.empty(x.shape, dtype=np.float64)
+    out[:, 0] = -(x[:, 1] - 0.5)
+    out[:, 1] = x[:, 0] - 0.5
+    return out
+
+
+def test_hyperbolic_flow_sweep_is_a_direct_solve(rb):
+    """Advection-reaction without diffusion: in the topological order of the upwind graph B is block lower triangular, the
+    flow-ordered block Gauss-Seidel sweep solves it; block Jacobi needed hundreds of iterations."""
+    from oracle import dg_oracle
+    name = "hyperbolic"
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(16384, tiles=4, seed=3), subtriangulation="fan")
+    dg = rb.DGFEM(geo, polynomial_degree=2)
+    dg.add_data(**PROBLEMS[name]["data"])
+    dg.dgfem(solve=True)
+    si = dg.solve_info
+    assert si["preconditioner"] == "sweep" and si["converged"] and si["flow_cycles_broken"] == 0, si
+    assert si["iterations"] <= 5, si
+    B, L, info = dg_oracle.assemble(geo, 2, **PROBLEMS[name]["data"])
+    xo = dg_oracle.solve(B, L)
+    assert util.rel_l2(dg.solution, xo) <= util.TOL_SOLUTION, si
+    # the same system with plain block Jacobi: same solution, many more iterations
+    dg.solver_options.update(preconditioner="bj")
+    dg.dgfem(solve=True)
+    assert dg.solve_info["preconditioner"] == "bj"
+    assert util.rel_l2(dg.solution, xo) <= util.TOL_SOLUTION
+    assert dg.solve_info["iterations"] > 100
+
+
+def _rotating(x):
+    out = np.empty(x.shape, dtype=np.float64)
+    out[:, 0] = -(x[:, 1] - 0.5)
+    out[:, 1] = x[:, 0] - 0.5
+    return out
+
+
+@pytest.mark.parametrize("E", [400, 4000])
+def test_flow_sweep_with_closed_streamlines_still_converges(rb, E):
+    """A rotating advection field: the upwind graph is all cycles.  They are broken at the elements with the fewest unresolved
+    upwind neighbours; the sweep is a preconditioner then (small mesh) or is dropped for block Jacobi when the resulting order
+    is nearly sequential (large mesh) -- either way the solve converges to the oracle's solution."""
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(rb.voronoi_mesh(E, seed=4), subtriangulation="fan")
+    data = dict(advection=_rotating, reaction=lambda x: np.full(x.shape[0], 2.0), forcing=lambda x: np.ones(x.shape[0]),
+                dirichlet_bcs=lambda x: np.zeros(x.shape[0]))
+    dg = rb.DGFEM(geo, polynomial_degree=1)
+    dg.add_data(**data)
+    dg.dgfem(solve=True)
+    assert dg.solve_info["converged"], dg.solve_info
+    assert dg.solve_info["preconditioner"] in ("sweep", "bj")
+    B, L, info = dg_oracle.assemble(geo, 1, **data)
+    assert util.rel_l2(dg.solution, dg_oracle.solve(B, L)) <= util.TOL_SOLUTION, dg.solve_info

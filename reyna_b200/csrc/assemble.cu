@@ -86,6 +86,7 @@ static int make_args(const char* who, const rb_geom* g, const rb_structure* s, c
     const int p = q->p;
     RB_REQUIRE(p >= 1 && p <= RB_MAX_P, RB_E_DEGREE, "reyna_b200_assemble: polynomial degree must be 1..3");
     const int n_vsegs = g->elem_seg0 ? g->n_vsegs : g->n_rows;
+    const int d = (p + 1) * (p + 2) / 2;
     RB_REQUIRE(workspace_bytes >= reyna_b200_assemble_workspace(g->n_elem, g->n_iface, n_vsegs, p), RB_E_WORKSPACE,
                "reyna_b200_assemble: workspace too small");
     // which terms are present is decided by the FACE samples when there are faces (the volume samples may still be on their
@@ -129,6 +130,8 @@ static int make_args(const char* who, const rb_geom* g, const rb_structure* s, c
     A.frec = reinterpret_cast<FaceRec*>(w);
     w += align16(sizeof(FaceRec) * nf);
     A.vdiag = reinterpret_cast<double*>(w);
+    w += align16(sizeof(double) * (size_t)(n_vsegs > 0 ? n_vsegs : 1) * ((size_t)d * d + d));
+    A.vol_next = reinterpret_cast<int*>(w);      // inside the 256 spare bytes of the workspace
     return 0;
 }
 

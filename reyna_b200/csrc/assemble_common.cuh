@@ -33,6 +33,7 @@ struct AsmArgs {
     const FaceRec* frec;   // [n_iface] flattened face geometry + SIPG penalty, written by dg_prepare_kernel
     const int32_t* adj_nb; // [n_items] neighbour element of every adjacency item (rb_structure.adj_nb)
     double* vdiag;         // [n_vsegs][d*d+d] per-segment volume sums (block + load): dg_volume_kernel -> dg_face_kernel
+    int* vol_next;             // round counter of the persistent volume kernel (workspace)
     int elem_lo, elem_hi;      // elements assembled by this launch (a range of whole volume rounds)
     int vround_lo, vround_hi;  // their volume rounds
 };

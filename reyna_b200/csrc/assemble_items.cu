@@ -31,7 +31,7 @@ constexpr int kWarp = 32;
 constexpr int kMaxSeg = 8;      // volume segments staged per face round
 constexpr int kWindow = 64;     // consecutive elements per face CTA
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kVolAhead = 148 * 12;   // volume rounds resident on the GPU: the round that far ahead is prefetched into L2
+constexpr int kVolWarps = kNumSMs * 11;   // persistent warps of the volume kernel (11 one-warp CTAs fit an SM)
 
 // ---- PTX: mbarrier + bulk async copies ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,33 +114,46 @@ __device__ __forceinline__ int pair_dst(int kk) {
 // =======================================================================================================================
 // volume kernel
 // =======================================================================================================================
+// Persistent warps: CTA b (one warp) takes the volume rounds b, b + gridDim, ...  The samples of a round live in TWO halves of
+// the shared-memory buffer (quadrature points [0, Q0) and [Q0, Qv)), each with its own mbarrier: as soon as the warp has
+// consumed a half it refills it with the NEXT round's data, so that in steady state a warp never waits for memory and no
+// second buffer is needed -- the copy of one half travels while the other half is being contracted.
 template <int P, int RS, bool DIFF, bool ADV>
 struct VolSmem {
     using DM = Dm<P, RS>;
-    static constexpr int SZA = DIFF ? DM::QV * 32 * 32 : 0;
-    static constexpr int SZB = ADV ? DM::QV * 32 * 16 : 0;
-    static constexpr int SZC = DM::QV * 32 * 8 + 16;
-    static constexpr int OA = 0, OB = OA + SZA, OC = OB + SZB, OF = OC + SZC, SAMPLES = OF + SZC;
+    static constexpr int QV = DM::QV, Q0 = (QV + 1) / 2, Q1 = QV - Q0;
+    static constexpr int a_bytes(int q) { return DIFF ? q * 32 * 32 : 0; }
+    static constexpr int b_bytes(int q) { return ADV ? q * 32 * 16 : 0; }
+    static constexpr int c_bytes(int q) { return q * 32 * 8 + 16; }          // 8-byte samples: 16 bytes of alignment slack
+    // half 0 | half 1, each: a, b, c, f
+    static constexpr int OA0 = 0, OB0 = OA0 + a_bytes(Q0), OC0 = OB0 + b_bytes(Q0), OF0 = OC0 + c_bytes(Q0), END0 = OF0 + c_bytes(Q0);
+    static constexpr int OA1 = END0, OB1 = OA1 + a_bytes(Q1), OC1 = OB1 + b_bytes(Q1), OF1 = OC1 + c_bytes(Q1), END1 = OF1 + c_bytes(Q1);
+    static constexpr int SAMPLES = END1, H1B = END1 - END0;
     static constexpr int PARTB = DM::NPAIR_MAX * kPartStride * 16;
-    // one pass: the partial blocks overwrite the consumed samples; several passes: the samples have to survive
-    static constexpr int OPART = RS == 1 ? 0 : SAMPLES;
-    static constexpr int OMETA = RS == 1 ? ((SAMPLES > PARTB ? SAMPLES : PARTB) + 15) / 16 * 16 : SAMPLES + PARTB;   // int s_start[36], s_seg[36]
+    // one part (RS == 1): the partial blocks are reduced through the consumed half 1, in NPASS passes of PP value pairs;
+    // several parts: the samples have to survive, the partials get a buffer of their own
+    static constexpr int NPASS = RS == 1 ? (PARTB + H1B - 1) / H1B : 1;
+    static constexpr int PP = (DM::NPAIR_MAX + NPASS - 1) / NPASS;
+    static constexpr int OPART = RS == 1 ? END0 : SAMPLES;
+    static constexpr int OMETA = (RS == 1 ? SAMPLES : SAMPLES + PARTB);       // int s_start[36], s_seg[36]
     static constexpr int OBAR = OMETA + 4 * 72;
     static constexpr int TOTAL = OBAR + 16;
+    static_assert(PP * kPartStride * 16 <= (RS == 1 ? H1B : PARTB), "partial buffer");
+    static_assert(END0 % 16 == 0 && OMETA % 16 == 0, "alignment");
 };
 
-// One pass over the quadrature points of the lane's triangle: rows [J0, J0+RJ) of the local block (+ the load in the last part).
-template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void volume_pass(const AsmArgs& A, const unsigned char* __restrict__ sm, int lane, int n, int hc, int hf,
-                                            const ElemBox& bx, double2 V0, double2 V1, double2 V2, double hdet, bool has_c,
-                                            bool has_f, double* __restrict__ acc) {
+// Quadrature points [QL, QH) of the lane's triangle from one half of the sample buffer: rows [J0, J0+RJ) of the local block
+// (+ the load in the last part).  O*: byte offsets of the half's arrays, hc / hf: where the 8-byte samples start in theirs.
+template <int P, int RS, int PART, bool DIFF, bool ADV, int QL, int QH, int OA, int OB, int OC, int OF>
+__device__ __forceinline__ void volume_points(const AsmArgs& A, const unsigned char* __restrict__ sm, int lane, int n, int hc, int hf,
+                                              const ElemBox& bx, double2 V0, double2 V1, double2 V2, double hdet, bool has_c,
+                                              bool has_f, double* __restrict__ acc) {
     using DM = Dm<P, RS>;
-    using S = VolSmem<P, RS, DIFF, ADV>;
-    constexpr int D = DM::D, RJ = DM::RJ, NB = DM::NB, QV = DM::QV, J0 = PART * RJ;
+    constexpr int D = DM::D, RJ = DM::RJ, NB = DM::NB, J0 = PART * RJ;
     constexpr bool LAST = PART == RS - 1;
 #pragma unroll 1
-    for (int q = 0; q < QV; ++q) {
-        const int idx = q * n + lane;
+    for (int q = QL; q < QH; ++q) {
+        const int idx = (q - QL) * n + lane;
         double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
         const double r0 = A.rvx[q], r1 = A.rvy[q];
         const double l0 = 1.0 - r0 - r1;
@@ -148,16 +161,16 @@ __device__ __forceinline__ void volume_pass(const AsmArgs& A, const unsigned cha
         const double y = l0 * V0.y + r0 * V1.y + r1 * V2.y;
         const double W = hdet * A.wv[q];
         if (DIFF) {
-            const double2 ra = *reinterpret_cast<const double2*>(sm + S::OA + (size_t)idx * 32);
-            const double2 rb = *reinterpret_cast<const double2*>(sm + S::OA + (size_t)idx * 32 + 16);
+            const double2 ra = *reinterpret_cast<const double2*>(sm + OA + (size_t)idx * 32);
+            const double2 rb = *reinterpret_cast<const double2*>(sm + OA + (size_t)idx * 32 + 16);
             a00 = W * ra.x; a01 = W * ra.y; a10 = W * rb.x; a11 = W * rb.y;
         }
         if (ADV) {
-            const double2 bb = *reinterpret_cast<const double2*>(sm + S::OB + (size_t)idx * 16);
+            const double2 bb = *reinterpret_cast<const double2*>(sm + OB + (size_t)idx * 16);
             b0 = W * bb.x; b1 = W * bb.y;
         }
-        const double cq = has_c ? W * *reinterpret_cast<const double*>(sm + S::OC + hc + (size_t)idx * 8) : 0.0;
-        const double wf = (LAST && has_f) ? W * *reinterpret_cast<const double*>(sm + S::OF + hf + (size_t)idx * 8) : 0.0;
+        const double cq = has_c ? W * *reinterpret_cast<const double*>(sm + OC + hc + (size_t)idx * 8) : 0.0;
+        const double wf = (LAST && has_f) ? W * *reinterpret_cast<const double*>(sm + OF + hf + (size_t)idx * 8) : 0.0;
         double phi[D], gx[D], gy[D];
         eval_basis<P, true>(x, y, bx, A.lc, phi, gx, gy);
         // column (trial i) quantities u = W * grad(phi_i)^T a, s = W * (b.grad(phi_i) + c phi_i)   (full_assembly.py:57-77)
@@ -199,121 +212,202 @@ __device__ __forceinline__ void volume_pass(const AsmArgs& A, const unsigned cha
     }
 }
 
+// Ordered per-segment sums of the lanes' partial blocks of one part -> vdiag, through the partial buffer in NPASS passes.
 template <int P, int RS, int PART, bool DIFF, bool ADV>
-__device__ __forceinline__ void volume_part(const AsmArgs& A, unsigned char* __restrict__ sm, int lane, int n, int hc, int hf,
-                                            bool active, const ElemBox& bx, double2 V0, double2 V1, double2 V2, double hdet,
-                                            bool has_c, bool has_f, int nseg) {
+__device__ __forceinline__ void volume_reduce(const AsmArgs& A, unsigned char* __restrict__ sm, int lane, bool active, int nseg,
+                                              const double* __restrict__ acc) {
     using DM = Dm<P, RS>;
     using S = VolSmem<P, RS, DIFF, ADV>;
     constexpr bool LAST = PART == RS - 1;
     constexpr int NVAL = DM::NB + (LAST ? DM::D : 0);
     constexpr int NP = (NVAL + 1) / 2;
-    double acc[2 * NP];
-#pragma unroll
-    for (int v = 0; v < 2 * NP; ++v) acc[v] = 0.0;
-    if (active) volume_pass<P, RS, PART, DIFF, ADV>(A, sm, lane, n, hc, hf, bx, V0, V1, V2, hdet, has_c, has_f, acc);
-    __syncwarp();                                   // every lane is done with the samples / the previous part's partials
     double2* part = reinterpret_cast<double2*>(sm + S::OPART);
-    if (active) {
-#pragma unroll
-        for (int kk = 0; kk < NP; ++kk) part[kk * kPartStride + lane] = make_double2(acc[2 * kk], acc[2 * kk + 1]);
-    }
-    __syncwarp();
     const int* s_start = reinterpret_cast<const int*>(sm + S::OMETA);
     const int* s_seg = s_start + 36;
-    const int total = nseg * NP;
-    for (int w = lane; w < total; w += kWarp) {
-        const int s = w / NP, kk = w - s * NP;
-        const int l0 = s_start[s], l1 = s_start[s + 1];
-        double2 v = part[kk * kPartStride + l0];
-        for (int l = l0 + 1; l < l1; l += 4) {      // triangles in order (main.py:315); four loads in flight (x + 0.0 = x)
-            double2 t[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) t[u] = l + u < l1 ? part[kk * kPartStride + l + u] : make_double2(0.0, 0.0);
+    for (int pass = 0; pass < S::NPASS; ++pass) {
+        constexpr int PPc = S::PP;
+        const int k0 = pass * PPc;
+        const int np = NP - k0 < PPc ? NP - k0 : PPc;      // pairs of this pass
+        if (np <= 0) break;
+        if (pass > 0) __syncwarp();                        // the previous pass has been read
+        if (active) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                v.x += t[u].x;
-                v.y += t[u].y;
-            }
+            for (int kk = 0; kk < PPc; ++kk)
+                if (k0 + kk < NP) part[kk * kPartStride + lane] = make_double2(acc[2 * (k0 + kk)], acc[2 * (k0 + kk) + 1]);
         }
-        double* dst = A.vdiag + (size_t)s_seg[s] * DM::NV + pair_dst<P, RS, PART>(kk);
-        if (2 * kk + 1 < NVAL) *reinterpret_cast<double2*>(dst) = v;
-        else *dst = v.x;
+        __syncwarp();
+        const int total = nseg * np;
+        for (int w = lane; w < total; w += kWarp) {
+            const int s = w / np, kk = w - s * np;
+            const int l0 = s_start[s], l1 = s_start[s + 1];
+            double2 v = part[kk * kPartStride + l0];
+            for (int l = l0 + 1; l < l1; l += 4) {      // triangles in order (main.py:315); four loads in flight (x + 0.0 = x)
+                double2 t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = l + u < l1 ? part[kk * kPartStride + l + u] : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    v.x += t[u].x;
+                    v.y += t[u].y;
+                }
+            }
+            double* dst = A.vdiag + (size_t)s_seg[s] * DM::NV + pair_dst<P, RS, PART>(k0 + kk);
+            if (2 * (k0 + kk) + 1 < NVAL) *reinterpret_cast<double2*>(dst) = v;
+            else *dst = v.x;
+        }
     }
+}
+
+// one lane: arm the half's mbarrier and start the bulk copies of quadrature points [QL, QH) of the round starting at triangle t0
+template <int P, int RS, bool DIFF, bool ADV, int QL, int QH, int OA, int OB, int OC, int OF>
+__device__ __forceinline__ void issue_half(const AsmArgs& A, unsigned char* __restrict__ sm, uint64_t* bar, int t0, int n) {
+    constexpr int QV = Dm<P, RS>::QV;
+    const bool has_c = A.c.vol_c != nullptr, has_f = A.c.vol_f != nullptr;
+    const size_t first = (size_t)QV * t0 + (size_t)QL * n;
+    const uint32_t cnt = (uint32_t)((QH - QL) * n);
+    const uintptr_t pc = reinterpret_cast<uintptr_t>(A.c.vol_c + first), pf = reinterpret_cast<uintptr_t>(A.c.vol_f + first);
+    const uint32_t hc = has_c ? (uint32_t)(pc & 15) : 0, hf = has_f ? (uint32_t)(pf & 15) : 0;
+    const uint32_t ba = DIFF ? cnt * 32 : 0, bb = ADV ? cnt * 16 : 0;
+    const uint32_t bc = has_c ? (hc + cnt * 8 + 15) & ~15u : 0, bf = has_f ? (hf + cnt * 8 + 15) & ~15u : 0;
+    mbar_expect_tx(bar, ba + bb + bc + bf);
+    if (DIFF) bulk_g2s(sm + OA, A.c.vol_a + 4 * first, ba, bar);
+    if (ADV) bulk_g2s(sm + OB, A.c.vol_b + 2 * first, bb, bar);
+    if (has_c) bulk_g2s(sm + OC, reinterpret_cast<const void*>(pc - hc), bc, bar);
+    if (has_f) bulk_g2s(sm + OF, reinterpret_cast<const void*>(pf - hf), bf, bar);
 }
 
 template <int P, int RS, bool DIFF, bool ADV>
 __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const __grid_constant__ AsmArgs A) {
     using DM = Dm<P, RS>;
     using S = VolSmem<P, RS, DIFF, ADV>;
-    constexpr int QV = DM::QV;
+    constexpr int QV = DM::QV, Q0 = S::Q0;
+    constexpr bool LASTP = true;
+    (void)LASTP;
     extern __shared__ __align__(128) unsigned char sm[];
     const int lane = threadIdx.x;
-    const int r = A.vround_lo + blockIdx.x;
-    const int t0 = A.g.vround_tri0[r];
-    const int n = A.g.vround_tri0[r + 1] - t0;
+    // rounds are handed out dynamically (A.vol_next, zeroed by the launcher): the warps of an SM do not run at the same speed
+    int r = A.vround_lo + blockIdx.x;
+    if (r >= A.vround_hi) return;
     const bool has_c = A.c.vol_c != nullptr, has_f = A.c.vol_f != nullptr;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + S::OBAR);
-    // 8-byte sample arrays: the round's range is widened to 16-byte boundaries, the data then starts hc / hf bytes in
-    const size_t first = (size_t)QV * t0;
-    const uintptr_t pc = reinterpret_cast<uintptr_t>(A.c.vol_c + first), pf = reinterpret_cast<uintptr_t>(A.c.vol_f + first);
-    const int hc = has_c ? (int)(pc & 15) : 0, hf = has_f ? (int)(pf & 15) : 0;
+    uint64_t* bar0 = reinterpret_cast<uint64_t*>(sm + S::OBAR);
+    uint64_t* bar1 = bar0 + 1;
+    int t0 = A.g.vround_tri0[r], t1 = A.g.vround_tri0[r + 1];
     if (lane == 0) {
-        mbar_init(bar, 1);
-        const uint32_t cnt = (uint32_t)(QV * n);
-        const uint32_t ba = DIFF ? cnt * 32 : 0, bb = ADV ? cnt * 16 : 0;
-        const uint32_t bc = has_c ? (hc + cnt * 8 + 15) & ~15u : 0, bf = has_f ? (hf + cnt * 8 + 15) & ~15u : 0;
-        mbar_expect_tx(bar, ba + bb + bc + bf);
-        if (DIFF) bulk_g2s(sm + S::OA, A.c.vol_a + 4 * first, ba, bar);
-        if (ADV) bulk_g2s(sm + S::OB, A.c.vol_b + 2 * first, bb, bar);
-        if (has_c) bulk_g2s(sm + S::OC, reinterpret_cast<const void*>(pc - hc), bc, bar);
-        if (has_f) bulk_g2s(sm + S::OF, reinterpret_cast<const void*>(pf - hf), bf, bar);
-    }
-    // the round that will take this slot of the GPU next: its samples are pulled into L2 below (its TMA then sees L2 latency)
-    const int rn = r + kVolAhead;
-    int u0 = 0, u1 = 0;
-    if (lane == 0 && rn < A.vround_hi) {
-        u0 = A.g.vround_tri0[rn];
-        u1 = A.g.vround_tri0[rn + 1];
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        issue_half<P, RS, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, bar0, t0, t1 - t0);
+        issue_half<P, RS, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, bar1, t0, t1 - t0);
     }
     __syncwarp();
-    const bool active = lane < n;
-    const int t = t0 + (active ? lane : 0);
-    const int e = A.g.tri_elem[t];
-    const int seg = A.g.tri_seg ? A.g.tri_seg[t] : e;
-    const ElemBox bx = A.ebox[e];
-    const double2* xy = reinterpret_cast<const double2*>(A.g.tri_xy) + 3 * (size_t)t;
-    const double2 V0 = xy[0], V1 = xy[1], V2 = xy[2];
-    // segments (= elements, or pieces of an element with more than 32 triangles) of the round
-    const int prev = __shfl_up_sync(kFull, seg, 1);
-    const bool head = active && (lane == 0 || seg != prev);
-    const unsigned hm = __ballot_sync(kFull, head);
-    const int nseg = __popc(hm);
-    {
-        int* s_start = reinterpret_cast<int*>(sm + S::OMETA);
-        int* s_seg = s_start + 36;
-        if (head) {
-            const int rank = __popc(hm & lanemask_lt());
-            s_start[rank] = lane;
-            s_seg[rank] = seg;
+    for (unsigned k = 0; r < A.vround_hi; ++k) {
+        const int n = t1 - t0;
+        // the next round of this warp (its triangle range is needed when the halves are refilled)
+        int rn = 0;
+        if (lane == 0) rn = A.vround_lo + (int)gridDim.x + atomicAdd(A.vol_next, 1);
+        rn = __shfl_sync(kFull, rn, 0);
+        const bool has_next = rn < A.vround_hi;
+        int tn0 = 0, tn1 = 0;
+        if (has_next) {
+            tn0 = A.g.vround_tri0[rn];
+            tn1 = A.g.vround_tri0[rn + 1];
         }
-        if (lane == 0) s_start[nseg] = n;
+        const bool active = lane < n;
+        const int t = t0 + (active ? lane : 0);
+        const int e = A.g.tri_elem[t];
+        const int seg = A.g.tri_seg ? A.g.tri_seg[t] : e;
+        const ElemBox bx = A.ebox[e];
+        const double2* xy = reinterpret_cast<const double2*>(A.g.tri_xy) + 3 * (size_t)t;
+        const double2 V0 = xy[0], V1 = xy[1], V2 = xy[2];
+        // segments (= elements, or pieces of an element with more than 32 triangles) of the round
+        const int prev = __shfl_up_sync(kFull, seg, 1);
+        const bool head = active && (lane == 0 || seg != prev);
+        const unsigned hm = __ballot_sync(kFull, head);
+        const int nseg = __popc(hm);
+        {
+            int* s_start = reinterpret_cast<int*>(sm + S::OMETA);
+            int* s_seg = s_start + 36;
+            if (head) {
+                const int rank = __popc(hm & lanemask_lt());
+                s_start[rank] = lane;
+                s_seg[rank] = seg;
+            }
+            if (lane == 0) s_start[nseg] = n;
+        }
+        // where the 8-byte samples start inside their (16-byte aligned) copies
+        const size_t f0 = (size_t)QV * t0, f1 = f0 + (size_t)Q0 * n;
+        const int hc0 = has_c ? (int)(reinterpret_cast<uintptr_t>(A.c.vol_c + f0) & 15) : 0;
+        const int hc1 = has_c ? (int)(reinterpret_cast<uintptr_t>(A.c.vol_c + f1) & 15) : 0;
+        const int hf0 = has_f ? (int)(reinterpret_cast<uintptr_t>(A.c.vol_f + f0) & 15) : 0;
+        const int hf1 = has_f ? (int)(reinterpret_cast<uintptr_t>(A.c.vol_f + f1) & 15) : 0;
+        // |det(0.5*[V1-V0; V2-V0])| (full_assembly.py:40-41); the extra 0.5 is the `0.5 * z` of :75-77
+        const double e1x = 0.5 * (V1.x - V0.x), e1y = 0.5 * (V1.y - V0.y);
+        const double e2x = 0.5 * (V2.x - V0.x), e2y = 0.5 * (V2.y - V0.y);
+        const double hdet = 0.5 * fabs(e1x * e2y - e1y * e2x);
+        const uint32_t parity = k & 1u;
+
+        if (RS == 1) {
+            double acc[2 * DM::NPAIR_MAX];
+#pragma unroll
+            for (int v = 0; v < 2 * DM::NPAIR_MAX; ++v) acc[v] = 0.0;
+            mbar_wait(bar0, parity);
+            if (active)
+                volume_points<P, RS, 0, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, bx, V0, V1, V2, hdet,
+                                                                                       has_c, has_f, acc);
+            __syncwarp();                           // half 0 is consumed: it takes the next round's points [0, Q0)
+            if (has_next && lane == 0)
+                issue_half<P, RS, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, bar0, tn0, tn1 - tn0);
+            mbar_wait(bar1, parity);
+            if (active)
+                volume_points<P, RS, 0, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, bx, V0, V1, V2, hdet,
+                                                                                        has_c, has_f, acc);
+            __syncwarp();                           // half 1 is consumed: the partial blocks are reduced through it
+            volume_reduce<P, RS, 0, DIFF, ADV>(A, sm, lane, active, nseg, acc);
+            fence_async_smem();                     // generic writes of the partial buffer before the async refill
+            __syncwarp();
+            if (has_next && lane == 0)
+                issue_half<P, RS, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, bar1, tn0, tn1 - tn0);
+        } else {
+            // several row parts: every part sweeps all points, the buffer is refilled when the round is done
+            mbar_wait(bar0, parity);
+            mbar_wait(bar1, parity);
+            {
+                double acc[2 * ((DM::NB + 1) / 2)];
+#pragma unroll
+                for (int v = 0; v < 2 * ((DM::NB + 1) / 2); ++v) acc[v] = 0.0;
+                if (active) {
+                    volume_points<P, RS, 0, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, bx, V0, V1, V2,
+                                                                                           hdet, has_c, has_f, acc);
+                    volume_points<P, RS, 0, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, bx, V0, V1, V2,
+                                                                                            hdet, has_c, has_f, acc);
+                }
+                __syncwarp();
+                volume_reduce<P, RS, 0, DIFF, ADV>(A, sm, lane, active, nseg, acc);
+            }
+            {
+                double acc[2 * DM::NPAIR_MAX];
+#pragma unroll
+                for (int v = 0; v < 2 * DM::NPAIR_MAX; ++v) acc[v] = 0.0;
+                if (active) {
+                    volume_points<P, RS, RS - 1, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, bx, V0, V1, V2,
+                                                                                                hdet, has_c, has_f, acc);
+                    volume_points<P, RS, RS - 1, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, bx, V0, V1,
+                                                                                                 V2, hdet, has_c, has_f, acc);
+                }
+                __syncwarp();
+                volume_reduce<P, RS, RS - 1, DIFF, ADV>(A, sm, lane, active, nseg, acc);
+            }
+            __syncwarp();
+            if (has_next && lane == 0) {
+                issue_half<P, RS, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, bar0, tn0, tn1 - tn0);
+                issue_half<P, RS, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, bar1, tn0, tn1 - tn0);
+            }
+        }
+        __syncwarp();                               // the round's segment table may be overwritten
+        r = rn;
+        t0 = tn0;
+        t1 = tn1;
     }
-    mbar_wait(bar, 0);
-    if (u1 > u0) {
-        const uint32_t cn = (uint32_t)(QV * (u1 - u0));
-        const size_t fn = (size_t)QV * u0;
-        if (DIFF) bulk_prefetch_l2(A.c.vol_a + 4 * fn, cn * 32);
-        if (ADV) bulk_prefetch_l2(A.c.vol_b + 2 * fn, cn * 16);
-        if (has_c) bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(A.c.vol_c + fn) & ~(uintptr_t)15), (cn * 8 + 15) & ~15u);
-        if (has_f) bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(A.c.vol_f + fn) & ~(uintptr_t)15), (cn * 8 + 15) & ~15u);
-    }
-    // |det(0.5*[V1-V0; V2-V0])| (full_assembly.py:40-41); the extra 0.5 is the `0.5 * z` of :75-77
-    const double e1x = 0.5 * (V1.x - V0.x), e1y = 0.5 * (V1.y - V0.y);
-    const double e2x = 0.5 * (V2.x - V0.x), e2y = 0.5 * (V2.y - V0.y);
-    const double hdet = 0.5 * fabs(e1x * e2y - e1y * e2x);
-    volume_part<P, RS, 0, DIFF, ADV>(A, sm, lane, n, hc, hf, active, bx, V0, V1, V2, hdet, has_c, has_f, nseg);
-    if (RS > 1) volume_part<P, RS, RS - 1, DIFF, ADV>(A, sm, lane, n, hc, hf, active, bx, V0, V1, V2, hdet, has_c, has_f, nseg);
 }
 
 // =======================================================================================================================
@@ -832,7 +926,9 @@ static int launch(const AsmArgs& A, cudaStream_t st) {
     RB_CUDA(cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS::TOTAL));
     RB_CUDA(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS::TOTAL));
     if (A.vround_hi > A.vround_lo) {
-        vk<<<A.vround_hi - A.vround_lo, kWarp, VS::TOTAL, st>>>(A);
+        const int nrounds = A.vround_hi - A.vround_lo;
+        RB_CUDA(cudaMemsetAsync(A.vol_next, 0, sizeof(int), st));
+        vk<<<nrounds < kVolWarps ? nrounds : kVolWarps, kWarp, VS::TOTAL, st>>>(A);
         RB_LAUNCH_CHECK("dg_volume_kernel");
     }
     const int blocks = (int)div_up(A.elem_hi - A.elem_lo, kWindow);

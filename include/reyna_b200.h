@@ -75,7 +75,14 @@ typedef struct {
     const int32_t *elem_seg0;  /* [n_rows+1] first segment of every element; NULL = identity                  */
     int32_t n_vrounds;
     int32_t n_vsegs;           /* number of segments (== n_rows when elem_seg0 is NULL)                       */
+    const void *tables;        /* geometry tables written once per geometry by reyna_b200_geometry_tables() (basis scalings
+                                  of every element, flattened face geometry, |k_b|_K of the penalty): with them the
+                                  per-assembly prepass only computes the SIPG penalties; NULL = it computes everything */
 } rb_geom;
+
+/* Geometry-only tables of the assembly (they depend on nodes / faces / polygons, not on coefficients or the degree). */
+size_t reyna_b200_geometry_tables_bytes(int32_t n_elem, int32_t n_iface);
+int reyna_b200_geometry_tables(const rb_geom *g, void *tables, size_t tables_bytes, void *stream);
 
 /* Reference quadrature (HOST arrays; DGFEM._intialise_quadrature, main.py:233-257). */
 typedef struct {

@@ -19,7 +19,7 @@ EXPORTS = (
     "reyna_b200_structure_workspace", "reyna_b200_structure", "reyna_b200_structure_known", "reyna_b200_csr_pattern", "reyna_b200_csr_pattern_local",
     "reyna_b200_nccl_unique_id", "reyna_b200_comm_create", "reyna_b200_comm_destroy", "reyna_b200_dist_create", "reyna_b200_dist_destroy", "reyna_b200_dist_counters",
     "reyna_b200_nccl_halo", "reyna_b200_nccl_allreduce",
-    "reyna_b200_assemble_workspace", "reyna_b200_assemble", "reyna_b200_assemble_prepare", "reyna_b200_assemble_range",
+    "reyna_b200_geometry_tables_bytes", "reyna_b200_geometry_tables", "reyna_b200_assemble_workspace", "reyna_b200_assemble", "reyna_b200_assemble_prepare", "reyna_b200_assemble_range",
     "reyna_b200_boundary", "reyna_b200_compact_workspace", "reyna_b200_compact_count", "reyna_b200_compact_fill",
     "reyna_b200_mg_create", "reyna_b200_mg_destroy", "reyna_b200_mg_info", "reyna_b200_mg_apply",
     "reyna_b200_solve_workspace", "reyna_b200_solve", "reyna_b200_spmv", "reyna_b200_errors_workspace",
@@ -33,7 +33,7 @@ class RbGeom(C.Structure):
                [(n, C.c_void_p) for n in ("nodes", "tri", "tri_elem", "tri_off", "bbox", "area", "poly_off", "poly_vtx",
                                           "iedge", "ielem", "inorm", "bedge", "belem", "bnorm", "elem_gid",
                                           "tri_xy", "vround_tri0", "tri_seg", "elem_seg0")] + \
-               [(n, C.c_int32) for n in ("n_vrounds", "n_vsegs")]
+               [(n, C.c_int32) for n in ("n_vrounds", "n_vsegs")] + [("tables", C.c_void_p)]
 
 
 class RbQuad(C.Structure):
@@ -138,6 +138,10 @@ def lib() -> C.CDLL:
     L.reyna_b200_assemble.restype = C.c_int
     L.reyna_b200_assemble.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.POINTER(RbCoefs), C.POINTER(RbQuad),
                                       C.c_double, vp, vp, i64p, vp, C.c_size_t, vp]
+    L.reyna_b200_geometry_tables_bytes.restype = C.c_size_t
+    L.reyna_b200_geometry_tables_bytes.argtypes = [i32, i32]
+    L.reyna_b200_geometry_tables.restype = C.c_int
+    L.reyna_b200_geometry_tables.argtypes = [C.POINTER(RbGeom), vp, C.c_size_t, vp]
     L.reyna_b200_assemble_prepare.restype = C.c_int
     L.reyna_b200_assemble_prepare.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.POINTER(RbCoefs), C.POINTER(RbQuad),
                                               C.c_double, vp, C.c_size_t, vp]

@@ -64,17 +64,86 @@ __global__ void __launch_bounds__(256) dg_prepare_faces_kernel(rb_geom g, const 
     }
 }
 
+// geometry tables (once per geometry): the face record without the penalty, and |k_b|_K of both elements of every face
+__global__ void __launch_bounds__(256) dg_geometry_faces_kernel(rb_geom g, FaceRec* __restrict__ frec, double2* __restrict__ fkb) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.n_iface; f += stride) {
+        const double2 P0 = reinterpret_cast<const double2*>(g.nodes)[g.iedge[2 * (size_t)f]];
+        const double2 P1 = reinterpret_cast<const double2*>(g.nodes)[g.iedge[2 * (size_t)f + 1]];
+        const double2 n = reinterpret_cast<const double2*>(g.inorm)[f];
+        const double ex = P1.x - P0.x, ey = P1.y - P0.y;
+        const double tx = 0.5 * ex, ty = 0.5 * ey;
+        const int e1 = g.ielem[2 * (size_t)f], e2 = g.ielem[2 * (size_t)f + 1];
+        fkb[f] = make_double2(max_sub_area_g(g, e1, P0, ex, ey), max_sub_area_g(g, e2, P0, ex, ey));
+        FaceRec r;
+        r.midx = (P0.x + P1.x) * 0.5; r.midy = (P0.y + P1.y) * 0.5;     // same expressions as dg_prepare_faces_kernel
+        r.tanx = tx; r.tany = ty;
+        r.nx = n.x; r.ny = n.y;
+        r.De = sqrt(tx * tx + ty * ty); r.sigma = 0.0;
+        frec[f] = r;
+    }
+}
+
+// per-assembly prepass when the geometry tables exist: only the SIPG penalty depends on the coefficients
+__global__ void __launch_bounds__(256) dg_face_sigma_kernel(rb_geom g, const double* __restrict__ if_a_mid, double sigma_pp, double p2,
+                                                            const FaceRec* __restrict__ frec, const double2* __restrict__ fkb,
+                                                            double* __restrict__ fsigma) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.n_iface; f += stride) {
+        const double2 n = make_double2(frec[f].nx, frec[f].ny);
+        const double De = frec[f].De;
+        const int e1 = g.ielem[2 * (size_t)f], e2 = g.ielem[2 * (size_t)f + 1];
+        const double2 m0 = reinterpret_cast<const double2*>(if_a_mid)[2 * (size_t)f];
+        const double2 m1 = reinterpret_cast<const double2*>(if_a_mid)[2 * (size_t)f + 1];
+        const double lam = (n.x * m0.x + n.y * m1.x) * n.x + (n.x * m0.y + n.y * m1.y) * n.y;   // full_assembly.py:140
+        const double a1 = g.area[e1], a2 = g.area[e2];
+        const double2 kb = fkb[f];
+        const double c1 = fmin(a1 / kb.x, p2);
+        const double c2 = fmin(a2 / kb.y, p2);
+        fsigma[f] = sigma_pp * lam * (2.0 * De) * fmax(c1 / a1, c2 / a2);        // full_assembly.py:146-148
+    }
+}
+
 }  // namespace rb
 
 using namespace rb;
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+extern "C" size_t reyna_b200_geometry_tables_bytes(int32_t n_elem, int32_t n_iface) {
+    const size_t ne = (size_t)(n_elem > 0 ? n_elem : 1), nf = (size_t)(n_iface > 0 ? n_iface : 1);
+    return align16(sizeof(ElemBox) * ne) + align16(sizeof(FaceRec) * nf) + align16(sizeof(double2) * nf) + 16;
+}
+
+extern "C" int reyna_b200_geometry_tables(const rb_geom* g, void* tables, size_t tables_bytes, void* stream) {
+    RB_REQUIRE(g && tables, RB_E_ARG, "reyna_b200_geometry_tables: null argument");
+    RB_REQUIRE(((uintptr_t)tables & 15) == 0 && tables_bytes >= reyna_b200_geometry_tables_bytes(g->n_elem, g->n_iface), RB_E_WORKSPACE,
+               "reyna_b200_geometry_tables: buffer too small or not 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ne = (size_t)(g->n_elem > 0 ? g->n_elem : 1), nf = (size_t)(g->n_iface > 0 ? g->n_iface : 1);
+    uintptr_t w = (uintptr_t)tables;
+    ElemBox* ebox = reinterpret_cast<ElemBox*>(w);
+    w += align16(sizeof(ElemBox) * ne);
+    FaceRec* frec = reinterpret_cast<FaceRec*>(w);
+    w += align16(sizeof(FaceRec) * nf);
+    double2* fkb = reinterpret_cast<double2*>(w);
+    if (g->n_elem > 0) {
+        dg_prepare_boxes_kernel<<<grid_for(g->n_elem, 256, kNumSMs * 8), 256, 0, st>>>(*g, ebox);
+        RB_LAUNCH_CHECK("dg_prepare_boxes_kernel");
+    }
+    if (g->n_iface > 0) {
+        dg_geometry_faces_kernel<<<grid_for(g->n_iface, 256, kNumSMs * 8), 256, 0, st>>>(*g, frec, fkb);
+        RB_LAUNCH_CHECK("dg_geometry_faces_kernel");
+    }
+    return 0;
+}
+
 extern "C" size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface, int32_t n_vsegs, int32_t p) {
     const size_t ne = (size_t)(n_elem > 0 ? n_elem : 1), nf = (size_t)(n_iface > 0 ? n_iface : 1);
     const size_t ns = (size_t)(n_vsegs > 0 ? n_vsegs : 1);
     const size_t d = (size_t)(p + 1) * (p + 2) / 2;
-    return align16(sizeof(ElemBox) * ne) + align16(sizeof(FaceRec) * nf) + align16(sizeof(double) * ns * (d * d + d)) + 256;
+    return align16(sizeof(ElemBox) * ne) + align16(sizeof(FaceRec) * nf) + align16(sizeof(double) * ns * (d * d + d)) +
+           align16(sizeof(double) * nf) + 256;
 }
 
 // Shared argument check + kernel argument block of the three entry points below.
@@ -131,12 +200,35 @@ static int make_args(const char* who, const rb_geom* g, const rb_structure* s, c
     w += align16(sizeof(FaceRec) * nf);
     A.vdiag = reinterpret_cast<double*>(w);
     w += align16(sizeof(double) * (size_t)(n_vsegs > 0 ? n_vsegs : 1) * ((size_t)d * d + d));
+    double* fsigma = reinterpret_cast<double*>(w);
+    w += align16(sizeof(double) * nf);
     A.vol_next = reinterpret_cast<int*>(w);      // inside the 256 spare bytes of the workspace
+    A.fsigma = nullptr;
+    A.fkb = nullptr;
+    if (g->tables) {
+        // geometry tables of reyna_b200_geometry_tables(): boxes and face records are read from there, the prepass only
+        // computes the penalties (separate array: the cached records carry sigma = 0)
+        uintptr_t t = (uintptr_t)g->tables;
+        A.ebox = reinterpret_cast<const ElemBox*>(t);
+        t += align16(sizeof(ElemBox) * ne);
+        A.frec = reinterpret_cast<const FaceRec*>(t);
+        t += align16(sizeof(FaceRec) * nf);
+        A.fkb = reinterpret_cast<const double*>(t);
+        if (diff && g->n_iface > 0) A.fsigma = fsigma;
+    }
     return 0;
 }
 
 static int run_prepare(const AsmArgs& A, bool diff, cudaStream_t st) {
     const rb_geom& g = A.g;
+    if (g.tables) {
+        if (A.fsigma) {
+            dg_face_sigma_kernel<<<grid_for(g.n_iface, 256, kNumSMs * 8), 256, 0, st>>>(
+                g, A.c.if_a_mid, A.sigma_pp, A.p2, A.frec, reinterpret_cast<const double2*>(A.fkb), const_cast<double*>(A.fsigma));
+            RB_LAUNCH_CHECK("dg_face_sigma_kernel");
+        }
+        return 0;
+    }
     dg_prepare_boxes_kernel<<<grid_for(g.n_elem, 256, kNumSMs * 8), 256, 0, st>>>(g, const_cast<ElemBox*>(A.ebox));
     RB_LAUNCH_CHECK("dg_prepare_boxes_kernel");
     if (g.n_iface > 0) {

@@ -33,6 +33,8 @@ struct AsmArgs {
     const FaceRec* frec;   // [n_iface] flattened face geometry + SIPG penalty, written by dg_prepare_kernel
     const int32_t* adj_nb; // [n_items] neighbour element of every adjacency item (rb_structure.adj_nb)
     double* vdiag;         // [n_vsegs][d*d+d] per-segment volume sums (block + load): dg_volume_kernel -> dg_face_kernel
+    const double* fsigma;      // [n_iface] SIPG penalties when the face records come from the geometry tables (else in frec)
+    const double* fkb;         // [n_iface][2] |k_b|_K of both elements of a face (geometry tables)
     int* vol_next;             // round counter of the persistent volume kernel (workspace)
     int elem_lo, elem_hi;      // elements assembled by this launch (a range of whole volume rounds)
     int vround_lo, vround_hi;  // their volume rounds

@@ -430,7 +430,7 @@ struct FaceSmem {
     static constexpr int NT = P <= 2 ? 1 : 2;                                   // row-owner tasks per lane
     static constexpr int MAXE = (kWarp * NT) / DM::D < 8 ? (kWarp * NT) / DM::D : 8;   // elements per round
     static constexpr int NPL = 8 + 3 * DM::QE;                  // 16-byte planes per item: record 4, neighbour box 4, a 2/point, b 1/point
-    static constexpr int PLANES = NPL * 512;
+    static constexpr int PLANES = NPL * 512 + 256;               // + one 8-byte plane: penalties of the geometry-table path
     static constexpr int OOWN = PLANES;                          // own boxes of the round's elements [MAXE][64 bytes]
     static constexpr int OVD = OOWN + MAXE * 64;                 // volume sums of the round's segments [kMaxSeg][NV]
     static constexpr int STAGE = OVD + kMaxSeg * DM::NV * 8;     // the staging buffer
@@ -506,6 +506,7 @@ __device__ __forceinline__ void stage_round(const AsmArgs& A, unsigned char* __r
             __pipeline_memcpy_async(dst + k * 512, rec + k, 16);
             __pipeline_memcpy_async(dst + (4 + k) * 512, box + k, 16);
         }
+        if (A.fsigma) __pipeline_memcpy_async(sb + S::NPL * 512 + lane * 8, A.fsigma + f, 8);
 #pragma unroll
         for (int q = 0; q < QE; ++q) {
             const size_t m = (size_t)q * F + f;
@@ -591,6 +592,7 @@ __device__ __forceinline__ void face_sweep(const AsmArgs& A, const unsigned char
                 const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 512);
                 const double2 cc = *reinterpret_cast<const double2*>(p + 1024), d = *reinterpret_cast<const double2*>(p + 1536);
                 g.midx = a.x; g.midy = a.y; g.tanx = b.x; g.tany = b.y; g.nx = cc.x; g.ny = cc.y; g.De = d.x; g.sigma = d.y;
+                if (A.fsigma) g.sigma = *reinterpret_cast<const double*>(sb + S::NPL * 512 + lane * 8);
             }
             const ElemBox bxe = lds_box(sb + S::OOWN + c.el * 64, 16);
             const ElemBox bxo = lds_box(sb + 4 * 512 + lane * 16, 512);

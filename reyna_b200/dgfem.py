@@ -349,6 +349,19 @@ class DGFEM:
             for n in ('tri_xy', 'vround_tri0', 'tri_seg', 'elem_seg0'):
                 a = getattr(vs, n)
                 cache[key][n] = torch.from_numpy(a).to(dev) if a is not None else None
+            # geometry-only tables of the assembly (basis scalings, flattened faces, |k_b|_K): once per geometry and device
+            L = _lib.lib()
+            E = fg.n_elem
+            g = _lib.RbGeom(n_nodes=fg.n_nodes, n_elem=E, n_rows=getattr(fg, 'n_rows', E), n_tri=fg.n_tri, n_iface=fg.n_iface,
+                            n_bface=fg.n_bface, n_vrounds=vs.n_rounds, n_vsegs=vs.n_segs,
+                            **{k: _ptr(v) for k, v in cache[key].items()})
+            nbytes = L.reyna_b200_geometry_tables_bytes(E, fg.n_iface)
+            tables = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.reyna_b200_geometry_tables(C.byref(g), _ptr(tables), nbytes,
+                                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                           'reyna_b200_geometry_tables')
+            cache[key]['tables'] = tables
         return cache[key]
 
     def _quad_struct(self) -> "_lib.RbQuad":

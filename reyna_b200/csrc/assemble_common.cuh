@@ -36,6 +36,7 @@ struct AsmArgs {
     const double* fsigma;      // [n_iface] SIPG penalties when the face records come from the geometry tables (else in frec)
     const double* fkb;         // [n_iface][2] |k_b|_K of both elements of a face (geometry tables)
     int* vol_next;             // round counter of the persistent volume kernel (workspace)
+    int window;                // elements per CTA of the face kernel
     int elem_lo, elem_hi;      // elements assembled by this launch (a range of whole volume rounds)
     int vround_lo, vround_hi;  // their volume rounds
 };

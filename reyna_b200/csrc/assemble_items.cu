@@ -29,7 +29,7 @@ namespace items {
 
 constexpr int kWarp = 32;
 constexpr int kMaxSeg = 8;      // volume segments staged per face round
-constexpr int kWindow = 64;     // consecutive elements per face CTA
+constexpr int kWindow = 64;     // consecutive elements per face CTA at most (AsmArgs.window: 16..64, chosen by the launcher)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kVolWarps = kNumSMs * 11;   // persistent warps of the volume kernel (11 one-warp CTAs fit an SM)
 
@@ -697,8 +697,8 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
     constexpr int D = DM::D, DD = DM::DD, NV = DM::NV, RJ = DM::RJ, NB = DM::NB, NT = S::NT, MAXE = S::MAXE;
     extern __shared__ __align__(128) unsigned char sm[];
     const int lane = threadIdx.x;
-    const int e_beg = A.elem_lo + blockIdx.x * kWindow;
-    const int e_end = min(e_beg + kWindow, A.elem_hi);
+    const int e_beg = A.elem_lo + blockIdx.x * A.window;
+    const int e_end = min(e_beg + A.window, A.elem_hi);
     const int nw = e_end - e_beg;
     int* tab = reinterpret_cast<int*>(sm + S::OWIN);
     int *w_off = tab, *w_goff = tab + kTab, *w_sg = tab + 2 * kTab, *w_eg = tab + 3 * kTab, *w_round = tab + 4 * kTab;
@@ -933,7 +933,7 @@ static int launch(const AsmArgs& A, cudaStream_t st) {
         vk<<<nrounds < kVolWarps ? nrounds : kVolWarps, kWarp, VS::TOTAL, st>>>(A);
         RB_LAUNCH_CHECK("dg_volume_kernel");
     }
-    const int blocks = (int)div_up(A.elem_hi - A.elem_lo, kWindow);
+    const int blocks = (int)div_up(A.elem_hi - A.elem_lo, A.window);
     fk<<<blocks, kWarp, FS::TOTAL, st>>>(A);
     RB_LAUNCH_CHECK("dg_face_kernel");
     return 0;
@@ -951,7 +951,14 @@ static int dispatch(const AsmArgs& A, bool diff, bool adv, cudaStream_t st) {
 int items_max_face_items() { return items::kWarp; }
 int items_max_segments() { return items::kMaxSeg; }
 
-int launch_assemble_items(const AsmArgs& A, int p, bool diff, bool adv, cudaStream_t st) {
+int launch_assemble_items(const AsmArgs& A0, int p, bool diff, bool adv, cudaStream_t st) {
+    // elements per face CTA: at least ~6 waves of CTAs on the GPU (8 one-warp CTAs per SM) so that the last wave does not
+    // dominate small partitions, 16..64 elements
+    AsmArgs A = A0;
+    const int n = A.elem_hi - A.elem_lo;
+    int w = items::kWindow;
+    while (w > 16 && (int64_t)n < (int64_t)w * 6 * 8 * kNumSMs) w >>= 1;
+    A.window = w;
     switch (p) {
         case 1: return items::dispatch<1, 1>(A, diff, adv, st);
         case 2: return items::dispatch<2, 1>(A, diff, adv, st);

@@ -427,6 +427,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         torch.cuda.empty_cache()
         if ddg is not None:
             ddg.dgfem(solve=True)          # first distributed solve creates the NCCL communicator (not timed)
+        elif PROBLEMS[args.problem]["data"].get("diffusion") is None:
+            dg.dgfem(solve=True)           # first flow-ordered sweep compiles the host-side level builder with numba (not timed)
         barrier()
         ts = time.perf_counter()
         if ddg is not None:

@@ -8,9 +8,9 @@ from .mesh import PolyMesh, RectangleDomain, FlatRegions, voronoi_mesh, tiled_vo
 from .geometry import DGFEMGeometry, flat_geometry, save_geometry_cache, load_geometry_cache
 from .dgfem import DGFEM
 from .boundary_information import BoundaryInformation
-from .tools import evaluate, evaluate_batch
+from .tools import evaluate, evaluate_batch, plot_data, plot_DG
 from ._lib import ReynaB200Error, build, lib, LIB_PATH
 
 __version__ = "0.1.0"
 __all__ = ["PolyMesh", "RectangleDomain", "FlatRegions", "voronoi_mesh", "tiled_voronoi_mesh", "morton_order",
-           "DGFEMGeometry", "flat_geometry", "save_geometry_cache", "load_geometry_cache", "DGFEM", "BoundaryInformation", "evaluate", "evaluate_batch", "ReynaB200Error", "build", "lib", "LIB_PATH"]
+           "DGFEMGeometry", "flat_geometry", "save_geometry_cache", "load_geometry_cache", "DGFEM", "BoundaryInformation", "evaluate", "evaluate_batch", "plot_data", "plot_DG", "ReynaB200Error", "build", "lib", "LIB_PATH"]

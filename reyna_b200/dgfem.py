@@ -765,4 +765,5 @@ class DGFEM:
     def plot_DG(self):
         if self.solution is None:
             raise ValueError("Need to provide a solution using either the method '.dgfem' or an external function.")
-        raise NotImplementedError('plotting is outside the reyna_b200 hot path (needs matplotlib)')
+        from .tools import plot_DG
+        plot_DG(self.solution, self.geometry, self.polydegree)

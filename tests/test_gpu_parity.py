@@ -425,3 +425,31 @@ def test_element_with_more_than_32_faces_is_rejected(rb):
     dg.add_data(**PROBLEMS["adr"]["data"])
     with pytest.raises(rb.ReynaB200Error):
         dg.dgfem(solve=False)
+
+
+def test_plot_data_matches_the_reference_recipe(rb):
+    """plot_DG's data preparation (tools.py:15-114) batched on the device: vertex values, face colours and limits equal the
+    per-element recipe of the reference evaluated with the oracle basis."""
+    from oracle import dg_oracle
+    z, geo = util.load_golden("square64")
+    key = [str(c) for c in z["cases"] if str(c).endswith("_p2")][0]
+    name, p = util.split_case(key)
+    sol = z[key + "_solution"]
+    d = rb.plot_data(sol, geo, p)
+    orders = dg_oracle.basis_orders(p)
+    dim = orders.shape[0]
+    bb = np.asarray(geo.elem_bounding_boxes, dtype=float)
+    vals, means = [], []
+    for t in range(geo.n_elements):
+        node = geo.nodes[np.asarray(geo.mesh.filtered_regions[t])]
+        phi, _ = dg_oracle.basis_and_grad(node, np.repeat(bb[t][None], node.shape[0], axis=0), orders, need_grad=False)
+        u = sol[t * dim:(t + 1) * dim] @ phi                    # phi: (d, M)
+        vals.append(u)
+        means.append(u.mean())
+    u = np.concatenate(vals)
+    assert np.allclose(d["xyz"][:, 2], u, rtol=0, atol=1e-12 * np.abs(u).max())
+    s = max(abs(u.max()), abs(u.min()))
+    c = np.abs(np.array(means) / s)
+    assert np.allclose(d["facecolor"], np.column_stack((c, c, 1 - c)), atol=1e-12)
+    assert np.allclose(d["zlim"], (u.min(), u.max()), atol=1e-12 * s)
+    assert d["offsets"][-1] == d["xyz"].shape[0] and d["offsets"].shape[0] == geo.n_elements + 1

@@ -426,7 +426,7 @@ struct Solver {
     int sweep_levels = 0;
 
     int sweep_launch(const double* v, double* z) {
-        RB_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * (size_t)n, st));
+        RB_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * ((size_t)n + (size_t)ng), st));
         for (int l = 0; l < sweep_levels; ++l) {
             const int cnt = sweep_off[l + 1] - sweep_off[l];
             if (cnt <= 0) continue;
@@ -575,17 +575,20 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
     }
     s.use_graphs = (halo == nullptr);
     RB_LAUNCH_CHECK("block_jacobi_setup");
-    if (opts->sweep_levels > 0 && opts->sweep_elems && opts->sweep_level_off && !halo && !mg && opts->method != 0) {
-        // advection-reaction without diffusion: B is block triangular along the flow -> one sweep is (nearly) the solve
+    if (opts->sweep_levels > 0 && opts->sweep_elems && opts->sweep_level_off && !mg && opts->method != 0) {
+        // advection-reaction without diffusion: B is block triangular along the flow -> one sweep is (nearly) the solve.
+        // Partitioned (halo != NULL): the sweep covers the rank's own rows, ghost columns count as zero inside it.
         s.sweep_elems = opts->sweep_elems;
         s.sweep_off = opts->sweep_level_off;
         s.sweep_levels = opts->sweep_levels;
         if ((rc0 = s.sweep_launch(rhs, x))) return rc0;     // x0 = sweep(b): exact when the upwind graph has no cycle
+        s.use_graphs = true;                                // hundreds of tiny level launches and no collective inside: replay as a graph
     }
 
     int rc;
     const bool cg = opts->method == 0;
-    const int check = opts->check_every > 0 ? opts->check_every : 25;
+    int check = opts->check_every > 0 ? opts->check_every : 25;
+    if (s.sweep_levels > 0 && check > 2) check = 2;         // a sweep-preconditioned iteration is worth checking every other step
     double hS[S_COUNT];
     double bb = 0.0, target2 = 0.0;
     int it = 0, restarts = 0;
@@ -662,7 +665,7 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
         if (!(true_rr == true_rr)) { set_error("Krylov iteration produced NaN"); break; }
         if (true_rr <= target2) { done = true; break; }
         if (stagnated) break;                      // floor verified inside the last run (true_rr is the final residual)
-        if (s.sweep_levels > 0 && prev_true_rr < 0.0 && true_rr <= 1e-24 * (bb > 0.0 ? bb : 1.0)) {
+        if (s.sweep_levels > 0 && !halo && prev_true_rr < 0.0 && true_rr <= 1e-24 * (bb > 0.0 ? bb : 1.0)) {
             stagnated = true;                      // the flow sweep was a direct solve: x0 is at the rounding floor already
             break;
         }

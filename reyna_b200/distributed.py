@@ -10,7 +10,8 @@ The reference is a single-process program; this module 
   application), the piecewise-constant chain is GLOBAL and replicated (its rows are all-gathered once per solve, its
   right-hand side once per application), so the iteration counts do not grow with the number of GPUs.
 
-``torch.distributed`` (any backend) is only used to hand out the NCCL unique id and to gather the solution.
+``torch.distributed`` hands out the NCCL unique id, gathers the solution and -- for the multigrid set-up -- all-gathers CUDA
+tensors: the process group must use the NCCL backend (with gloo only ``preconditioner='bj'`` / ``'sweep'`` works).
 """
 from __future__ import annotations
 

@@ -424,10 +424,11 @@ class DGFEM:
             t2 = time.perf_counter()
             for (e_lo, e_hi, r_lo, r_hi) in self._chunks(fg, vs):
                 lo, hi = Q * int(vs.vround_tri0[r_lo]), Q * int(vs.vround_tri0[r_hi])
-                for key, fn, tail in terms:
-                    buf = self._staging(torch, key, (M + 1,) + tail)
-                    sampling.evaluate_batched(fn, Xs[lo:hi], tail, out=buf.numpy()[lo:hi])
-                    with torch.cuda.stream(s_in):
+                bufs = [self._staging(torch, key, (M + 1,) + tail) for key, _, tail in terms]
+                # all callables on a block of points while it is cache-resident
+                sampling.evaluate_many([(fn, tail, buf.numpy()[lo:hi]) for (key, fn, tail), buf in zip(terms, bufs)], Xs[lo:hi])
+                with torch.cuda.stream(s_in):
+                    for (key, _, _), buf in zip(terms, bufs):
                         cd[key][lo:hi].copy_(buf[lo:hi], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(s_in)

@@ -453,3 +453,19 @@ def test_plot_data_matches_the_reference_recipe(rb):
     assert np.allclose(d["facecolor"], np.column_stack((c, c, 1 - c)), atol=1e-12)
     assert np.allclose(d["zlim"], (u.min(), u.max()), atol=1e-12 * s)
     assert d["offsets"][-1] == d["xyz"].shape[0] and d["offsets"].shape[0] == geo.n_elements + 1
+
+
+@pytest.mark.parametrize("n_cells,name,p", [(1, "adr", 2), (1, "hyperbolic", 1), (3, "variable", 3), (4, "adr", 1)])
+def test_tiny_meshes(rb, n_cells, name, p):
+    """One to four elements (no or very few interior faces; a single interior edge is rejected like upstream leaves it undefined): windows, rounds and bulk stores at their smallest."""
+    from oracle import dg_oracle
+    xs = np.linspace(0.0, 1.0, n_cells + 1)
+    v = np.array([[x, y] for y in (0.0, 1.0) for x in xs])
+    regions = [np.array([i, i + 1, n_cells + 1 + i + 1, n_cells + 1 + i]) for i in range(n_cells)]
+    pts = np.array([[0.5 * (xs[i] + xs[i + 1]), 0.5] for i in range(n_cells)])
+    geo = rb.DGFEMGeometry(rb.PolyMesh(v, regions, pts, None))
+    dg = _run(rb, geo, name, p, solve=False)
+    B, L, info = dg_oracle.assemble(geo, p, **PROBLEMS[name]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY

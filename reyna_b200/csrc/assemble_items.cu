@@ -146,8 +146,8 @@ struct VolSmem {
 // (+ the load in the last part).  O*: byte offsets of the half's arrays, hc / hf: where the 8-byte samples start in theirs.
 template <int P, int RS, int PART, bool DIFF, bool ADV, int QL, int QH, int OA, int OB, int OC, int OF>
 __device__ __forceinline__ void volume_points(const AsmArgs& A, const unsigned char* __restrict__ sm, int lane, int n, int hc, int hf,
-                                              const PolyDir<P>& px, const PolyDir<P>& py, double2 V0, double2 V1, double2 V2,
-                                              double hdet, bool has_c, bool has_f, double* __restrict__ acc) {
+                                              const ElemBox& bx, double2 V0, double2 V1, double2 V2, double hdet, bool has_c,
+                                              bool has_f, double* __restrict__ acc) {
     using DM = Dm<P, RS>;
     constexpr int D = DM::D, RJ = DM::RJ, NB = DM::NB, J0 = PART * RJ;
     constexpr bool LAST = PART == RS - 1;
@@ -155,11 +155,9 @@ __device__ __forceinline__ void volume_points(const AsmArgs& A, const unsigned c
     for (int q = QL; q < QH; ++q) {
         const int idx = (q - QL) * n + lane;
         double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
-        // V0..V2 hold the BOX coordinates of the vertices: the point's box coordinates are the same affine combination as its
-        // physical ones (assembly_aux.py:7-29, 40-48); interior points of a sub-triangle lie strictly inside the box
         const double r0 = A.rvx[q], r1 = A.rvy[q];
         const double l0 = 1.0 - r0 - r1;
-        const double x = l0 * V0.x + r0 * V1.x + r1 * V2.x;
+        const double x = l0 * V0.x + r0 * V1.x + r1 * V2.x;      // assembly_aux.py:7-29
         const double y = l0 * V0.y + r0 * V1.y + r1 * V2.y;
         const double W = hdet * A.wv[q];
         if (DIFF) {
@@ -174,7 +172,7 @@ __device__ __forceinline__ void volume_points(const AsmArgs& A, const unsigned c
         const double cq = has_c ? W * *reinterpret_cast<const double*>(sm + OC + hc + (size_t)idx * 8) : 0.0;
         const double wf = (LAST && has_f) ? W * *reinterpret_cast<const double*>(sm + OF + hf + (size_t)idx * 8) : 0.0;
         double phi[D], gx[D], gy[D];
-        eval_basis_poly<P>(x, y, px, py, phi, gx, gy);
+        eval_basis<P, true>(x, y, bx, A.lc, phi, gx, gy);
         // column (trial i) quantities u = W * grad(phi_i)^T a, s = W * (b.grad(phi_i) + c phi_i)   (full_assembly.py:57-77)
 #pragma unroll
         for (int i = 0; i < D; ++i) {
@@ -346,12 +344,6 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
         const double e1x = 0.5 * (V1.x - V0.x), e1y = 0.5 * (V1.y - V0.y);
         const double e2x = 0.5 * (V2.x - V0.x), e2y = 0.5 * (V2.y - V0.y);
         const double hdet = 0.5 * fabs(e1x * e2y - e1y * e2x);
-        // the element's basis as polynomials in the box coordinates, and the box coordinates of the three vertices
-        const PolyDir<P> px = make_poly_dir<P>(bx.mx, bx.ihx, bx.s05x, bx.s15x, A.lc);
-        const PolyDir<P> py = make_poly_dir<P>(bx.my, bx.ihy, bx.s05y, bx.s15y, A.lc);
-        const double2 B0 = make_double2((V0.x - bx.mx) * bx.ihx, (V0.y - bx.my) * bx.ihy);
-        const double2 B1 = make_double2((V1.x - bx.mx) * bx.ihx, (V1.y - bx.my) * bx.ihy);
-        const double2 B2 = make_double2((V2.x - bx.mx) * bx.ihx, (V2.y - bx.my) * bx.ihy);
         const uint32_t parity = k & 1u;
 
         if (RS == 1) {
@@ -360,14 +352,14 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
             for (int v = 0; v < 2 * DM::NPAIR_MAX; ++v) acc[v] = 0.0;
             mbar_wait(bar0, parity);
             if (active)
-                volume_points<P, RS, 0, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, px, py, B0, B1, B2, hdet,
+                volume_points<P, RS, 0, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, bx, V0, V1, V2, hdet,
                                                                                        has_c, has_f, acc);
             __syncwarp();                           // half 0 is consumed: it takes the next round's points [0, Q0)
             if (has_next && lane == 0)
                 issue_half<P, RS, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, bar0, tn0, tn1 - tn0);
             mbar_wait(bar1, parity);
             if (active)
-                volume_points<P, RS, 0, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, px, py, B0, B1, B2, hdet,
+                volume_points<P, RS, 0, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, bx, V0, V1, V2, hdet,
                                                                                         has_c, has_f, acc);
             __syncwarp();                           // half 1 is consumed: the partial blocks are reduced through it
             volume_reduce<P, RS, 0, DIFF, ADV>(A, sm, lane, active, nseg, acc);
@@ -384,9 +376,9 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
 #pragma unroll
                 for (int v = 0; v < 2 * ((DM::NB + 1) / 2); ++v) acc[v] = 0.0;
                 if (active) {
-                    volume_points<P, RS, 0, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, px, py, B0, B1, B2,
+                    volume_points<P, RS, 0, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, bx, V0, V1, V2,
                                                                                            hdet, has_c, has_f, acc);
-                    volume_points<P, RS, 0, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, px, py, B0, B1, B2,
+                    volume_points<P, RS, 0, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, bx, V0, V1, V2,
                                                                                             hdet, has_c, has_f, acc);
                 }
                 __syncwarp();
@@ -397,10 +389,10 @@ __global__ void __launch_bounds__(kWarp, P <= 2 ? 12 : 1) dg_volume_kernel(const
 #pragma unroll
                 for (int v = 0; v < 2 * DM::NPAIR_MAX; ++v) acc[v] = 0.0;
                 if (active) {
-                    volume_points<P, RS, RS - 1, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, px, py, B0, B1, B2,
+                    volume_points<P, RS, RS - 1, DIFF, ADV, 0, Q0, S::OA0, S::OB0, S::OC0, S::OF0>(A, sm, lane, n, hc0, hf0, bx, V0, V1, V2,
                                                                                                 hdet, has_c, has_f, acc);
-                    volume_points<P, RS, RS - 1, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, px, py, B0, B1,
-                                                                                                 B2, hdet, has_c, has_f, acc);
+                    volume_points<P, RS, RS - 1, DIFF, ADV, Q0, QV, S::OA1, S::OB1, S::OC1, S::OF1>(A, sm, lane, n, hc1, hf1, bx, V0, V1,
+                                                                                                 V2, hdet, has_c, has_f, acc);
                 }
                 __syncwarp();
                 volume_reduce<P, RS, RS - 1, DIFF, ADV>(A, sm, lane, active, nseg, acc);

@@ -145,77 +145,4 @@ __device__ __forceinline__ void eval_basis(double x, double y, const ElemBox& bx
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// The same basis as polynomials in the box coordinate, with the element's scalings folded into per-direction coefficients
-// (computed once per element and lane): val_0 = k0, val_1 = k1 y, val_2 = a2 y^2 + c2, val_3 = y (a3 y^2 + c3),
-// der_1 = d1, der_2 = b2 y, der_3 = b3 y^2 + e3 -- 4 FP64 instructions per direction and point at P = 2 instead of ~15
-// (three-term recurrence + scalings).  Equal to leg1d up to rounding (the products are associated differently).
-// Used where the argument is strictly inside the box (interior quadrature points: the clamp of assembly_aux.py:50-54
-// cannot trigger).
-// ---------------------------------------------------------------------------------------------------------------------
-template <int P>
-struct PolyDir {
-    double m, ih;                 // y = (x - m) * ih
-    double k0, k1, a2, c2, a3, c3;
-    double d1, b2, b3, e3;
-};
-
-template <int P>
-__device__ __forceinline__ PolyDir<P> make_poly_dir(double m, double ih, double s05, double s15, const LegConst& lc) {
-    PolyDir<P> d;
-    d.m = m; d.ih = ih;
-    d.k0 = s05 * lc.c0[0];
-    d.k1 = s05 * lc.c1[0];
-    d.a2 = d.c2 = d.a3 = d.c3 = d.d1 = d.b2 = d.b3 = d.e3 = 0.0;
-    if (P >= 2) {
-        // v2 = (y v1 - aold1 v0) ianew1
-        d.a2 = s05 * (lc.c1[0] * lc.ianew[0][1]);
-        d.c2 = -s05 * (lc.aold[0][1] * lc.c0[0] * lc.ianew[0][1]);
-    }
-    if (P >= 3) {
-        // v3 = (y v2 - aold2 v1) ianew2
-        d.a3 = s05 * (lc.c1[0] * lc.ianew[0][1] * lc.ianew[0][2]);
-        d.c3 = -s05 * (lc.ianew[0][2] * (lc.aold[0][1] * lc.c0[0] * lc.ianew[0][1] + lc.aold[0][2] * lc.c1[0]));
-    }
-    if (P >= 1) d.d1 = (s15 * lc.corr[1]) * lc.c0[1];
-    if (P >= 2) d.b2 = (s15 * lc.corr[2]) * lc.c1[1];
-    if (P >= 3) {
-        // w2 = (y w1 - aold1' w0) ianew1'
-        d.b3 = (s15 * lc.corr[3]) * (lc.c1[1] * lc.ianew[1][1]);
-        d.e3 = -(s15 * lc.corr[3]) * (lc.aold[1][1] * lc.c0[1] * lc.ianew[1][1]);
-    }
-    return d;
-}
-
-template <int P>
-__device__ __forceinline__ void poly1d(double y, const PolyDir<P>& d, double (&val)[P + 1], double (&der)[P + 1]) {
-    const double y2 = y * y;
-    val[0] = d.k0;
-    der[0] = 0.0;
-    if (P >= 1) { val[1] = d.k1 * y; der[1] = d.d1; }
-    if (P >= 2) { val[2] = fma(d.a2, y2, d.c2); der[2] = d.b2 * y; }
-    if (P >= 3) { val[3] = y * fma(d.a3, y2, d.c3); der[3] = fma(d.b3, y2, d.e3); }
-}
-
-// phi, d/dx, d/dy of the D basis functions at box coordinates (xi, eta); same enumeration as eval_basis
-template <int P>
-__device__ __forceinline__ void eval_basis_poly(double xi, double eta, const PolyDir<P>& px, const PolyDir<P>& py,
-                                                double (&phi)[BasisDim<P>::D], double (&gx)[BasisDim<P>::D],
-                                                double (&gy)[BasisDim<P>::D]) {
-    double vx[P + 1], dx[P + 1], vy[P + 1], dy[P + 1];
-    poly1d<P>(xi, px, vx, dx);
-    poly1d<P>(eta, py, vy, dy);
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i <= P; ++i) {
-#pragma unroll
-        for (int j = 0; j <= P - i; ++j) {
-            phi[k] = vx[i] * vy[j];
-            gx[k] = i > 0 ? dx[i] * vy[j] : 0.0;
-            gy[k] = j > 0 ? vx[i] * dy[j] : 0.0;
-            ++k;
-        }
-    }
-}
-
 }  // namespace rb

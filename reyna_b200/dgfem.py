@@ -254,6 +254,9 @@ class DGFEM:
                 dev_t['if_upwind'] = torch.from_numpy(upw).to(dev)
                 nbytes += upw.nbytes
                 self._upwind_host = upw
+        elif self.advection is not None:
+            dev_t['if_upwind'] = torch.zeros(1, dtype=torch.uint8, device=dev)     # no interior face: nothing to flag
+            self._upwind_host = np.zeros(0, dtype=np.uint8)
         if fg.n_bface:
             mid, Xb = pts['mid_b'], pts['Xb']
             nbytes += self._put(torch, dev, dev_t, 'bf_g', self.dirichlet_bcs, Xb, ())

@@ -154,8 +154,9 @@ int reyna_b200_csr_pattern_local(const rb_geom *g, const rb_structure *s, int p,
  * DGFEM._interior_stiffness_matrix + int_localstiff, main.py:329-374 / full_assembly.py:80-214).
  * data [nnz], load [n_rows*d]; *zero_count (device int64, caller-zeroed) receives the number of exact zeros written.
  * workspace: reyna_b200_assemble_workspace() bytes of device scratch (per-element basis scalings, per-face records,
- * per-segment volume sums).  Limits of the item-per-lane kernels (RB_E_ARG otherwise): at most 32 contributing
- * interior faces per element (rb_structure.max_items) and at most 8 volume segments (256 sub-triangles) per element. */
+ * per-segment volume sums).  Limits (RB_E_ARG otherwise): at most 64 contributing interior faces per element
+ * (rb_structure.max_items; elements with more than 32 take a slower one-warp-per-element kernel) and at most 8 volume
+ * segments (256 sub-triangles) per element. */
 size_t reyna_b200_assemble_workspace(int32_t n_elem, int32_t n_iface, int32_t n_vsegs, int32_t p);
 int reyna_b200_assemble(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
                         double sigma_D, double *data, double *load, long long *zero_count, void *workspace,

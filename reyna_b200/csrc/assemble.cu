@@ -191,6 +191,7 @@ static int make_args(const char* who, const rb_geom* g, const rb_structure* s, c
     A.load = load;
     A.zero_count = reinterpret_cast<unsigned long long*>(zero_count);
     A.has_dups = s->n_dup_items > 0;
+    A.has_giants = s->max_items > items_max_face_items();
     // prepass tables and the volume sums (16-byte aligned slices of the workspace)
     const size_t ne = (size_t)(g->n_elem > 0 ? g->n_elem : 1), nf = (size_t)(g->n_iface > 0 ? g->n_iface : 1);
     uintptr_t w = ((uintptr_t)workspace + 15) & ~(uintptr_t)15;
@@ -253,8 +254,7 @@ static int run_range(AsmArgs& A, const rb_structure* s, int p, bool diff, bool a
                "reyna_b200_assemble: the geometry carries no volume stream (rb_geom.tri_xy / vround_tri0)");
     RB_REQUIRE((g.tri_seg == nullptr) == (g.elem_seg0 == nullptr), RB_E_ARG,
                "reyna_b200_assemble: tri_seg and elem_seg0 must be given together");
-    RB_REQUIRE(s->max_items <= items_max_face_items(), RB_E_ARG,
-               "reyna_b200_assemble: an element has more than 32 contributing interior faces");
+    RB_REQUIRE(s->max_items <= 64, RB_E_ARG, "reyna_b200_assemble: an element has more than 64 contributing interior faces");
     RB_REQUIRE(((uintptr_t)A.data & 15) == 0 && ((uintptr_t)A.load & 7) == 0, RB_E_ARG,
                "reyna_b200_assemble: data must be 16-byte aligned");
     const rb_coefs& c = A.c;

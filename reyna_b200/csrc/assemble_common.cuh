@@ -29,6 +29,7 @@ struct AsmArgs {
     double* load;
     unsigned long long* zero_count;
     int has_dups;      // adjacency contains merged (duplicate-neighbour) items
+    int has_giants;    // an element has more than 32 (element, face) items: dg_face_giant_kernel takes those
     const ElemBox* ebox;   // [n_elem]  bounding-box scalings, written by dg_prepare_kernel
     const FaceRec* frec;   // [n_iface] flattened face geometry + SIPG penalty, written by dg_prepare_kernel
     const int32_t* adj_nb; // [n_items] neighbour element of every adjacency item (rb_structure.adj_nb)

@@ -81,6 +81,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 }
 
 __device__ __forceinline__ int gid_of(const AsmArgs& A, int e) { return A.g.elem_gid ? A.g.elem_gid[e] : e; }
+__device__ __forceinline__ int seg0_of(const AsmArgs& A, int e) { return A.g.elem_seg0 ? A.g.elem_seg0[e] : e; }
 
 template <int P, int RS>
 struct Dm {
@@ -440,7 +441,7 @@ struct FaceSmem {
     static constexpr int OOUT = STAGE;                           // block rows of the round (+ 16 bytes of alignment shift)
     static constexpr int OPQ = OOUT;                             // the records live in the row buffer until the rows are written
     static constexpr int OWIN = OOUT + (OUTB > PQUVB ? OUTB : PQUVB);
-    static constexpr int TOTAL = OWIN + 5 * kTab * 4;            // window tables: adj_off, grp_off, first segment, gid, rounds
+    static constexpr int TOTAL = OWIN + 6 * kTab * 4;            // window tables: adj_off, grp_off, first segment, gid, round start / size
     static_assert(STAGE % 16 == 0 && OUTB % 16 == 0 && REC % 16 == 0, "alignment");
 };
 
@@ -456,10 +457,10 @@ struct Round {
 };
 
 __device__ __forceinline__ Round load_round(const int* __restrict__ tab, int r, int lane) {
-    const int *w_off = tab, *w_goff = tab + kTab, *w_sg = tab + 2 * kTab, *w_round = tab + 4 * kTab;
+    const int *w_off = tab, *w_goff = tab + kTab, *w_sg = tab + 2 * kTab, *w_round = tab + 4 * kTab, *w_rne = tab + 5 * kTab;
     Round x;
     x.e0 = w_round[r];
-    x.ne = w_round[r + 1] - x.e0;
+    x.ne = w_rne[r];
     const int i = x.e0 + (lane <= x.ne ? lane : 0);
     x.off = w_off[i];
     x.goff = w_goff[i];
@@ -475,8 +476,8 @@ struct Items {
 };
 
 __device__ __forceinline__ Items load_items(const AsmArgs& A, const int* __restrict__ tab, int r, int lane) {
-    const int *w_off = tab, *w_round = tab + 4 * kTab;
-    const int k0 = w_off[w_round[r]], k1 = w_off[w_round[r + 1]];
+    const int *w_off = tab, *w_round = tab + 4 * kTab, *w_rne = tab + 5 * kTab;
+    const int k0 = w_off[w_round[r]], k1 = w_off[w_round[r] + w_rne[r]];
     Items it;
     it.item = 0; it.nbr = 0;
     if (lane < k1 - k0) {
@@ -702,6 +703,7 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
     const int nw = e_end - e_beg;
     int* tab = reinterpret_cast<int*>(sm + S::OWIN);
     int *w_off = tab, *w_goff = tab + kTab, *w_sg = tab + 2 * kTab, *w_eg = tab + 3 * kTab, *w_round = tab + 4 * kTab;
+    int* w_rne = tab + 5 * kTab;
     // ---- window tables + the rounds of the window ---------------------------------------------------------------------------
     for (int i = lane; i <= nw; i += kWarp) {
         w_off[i] = A.adj_off[e_beg + i];
@@ -712,7 +714,6 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
     __syncwarp();
     int nr = 0;
     for (int e = 0; e < nw;) {
-        if (lane == 0) w_round[nr] = e;
         const int idx = e + lane;
         const bool in = idx <= nw && lane <= MAXE;
         const int off = in ? w_off[idx] : 0, sg = in ? w_sg[idx] : 0;
@@ -721,12 +722,19 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
         const bool ok = in && lane >= 1 && (off - k0 <= kWarp) && (sg - sg0 <= kMaxSeg);
         const unsigned m = __ballot_sync(kFull, ok) >> 1;
         const int ne = __ffs(~m) - 1;              // length of the run of set bits (both conditions are monotone)
-        if (ne == 0) __trap();                     // more than 32 items / kMaxSeg segments in one element: rejected by the host entry
+        if (ne == 0) {                             // an element with more than 32 items: assembled by dg_face_giant_kernel
+            ++e;
+            continue;
+        }
+        if (lane == 0) {
+            w_round[nr] = e;
+            w_rne[nr] = ne;
+        }
         e += ne;
         ++nr;
     }
-    if (lane == 0) w_round[nr] = nw;
     __syncwarp();
+    if (nr == 0) return;
     unsigned zeros = 0;
     unsigned char* sb = sm;
     unsigned char* pquv = sm + S::OPQ;
@@ -919,6 +927,227 @@ __global__ void __launch_bounds__(kWarp) dg_face_kernel(const __grid_constant__ 
 }
 
 // =======================================================================================================================
+// elements with more than 32 (element, face) items -- agglomerated / many-sided polygons.  Rare, so simple: one warp per such
+// element, items in chunks of 32 lanes read straight from global memory, two passes per item (diagonal contribution,
+// off-diagonal block); the diagonal partials are summed in item order through shared memory into a running sum (volume sums
+// first), the off-diagonal blocks go straight to their CSR slots.  dg_face_kernel leaves these elements out.
+// =======================================================================================================================
+template <int P, int RS, int PART, bool DIFF, bool ADV, bool OFF>
+__device__ __forceinline__ void giant_pass(const AsmArgs& A, int f, const FaceGeo& g, double sgn, bool down, const ElemBox& bxe,
+                                           const ElemBox& bxo, double* __restrict__ acc) {
+    using DM = Dm<P, RS>;
+    constexpr int D = DM::D, RJ = DM::RJ, QE = DM::QE, J0 = PART * RJ;
+    const size_t F = (size_t)A.g.n_iface;
+#pragma unroll 1
+    for (int q = 0; q < QE; ++q) {
+        const size_t m = (size_t)q * F + f;
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0, b0 = 0, b1 = 0;
+        if (DIFF) {
+            const double2 r0 = reinterpret_cast<const double2*>(A.c.if_a)[2 * m], r1 = reinterpret_cast<const double2*>(A.c.if_a)[2 * m + 1];
+            a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
+        }
+        if (ADV) {
+            const double2 bb = reinterpret_cast<const double2*>(A.c.if_b)[m];
+            b0 = bb.x; b1 = bb.y;
+        }
+        const double x = g.midx + A.xe[q] * g.tanx;
+        const double y = g.midy + A.xe[q] * g.tany;
+        const double W = g.De * A.we[q];
+        double atn0 = 0, atn1 = 0, gamma = 0;
+        if (DIFF) {
+            atn0 = g.nx * a00 + g.ny * a10;
+            atn1 = g.nx * a01 + g.ny * a11;
+        }
+        if (ADV) {
+            const double beta = b0 * g.nx + b1 * g.ny;
+            gamma = down ? -sgn * beta : 0.0;
+        }
+        const double hw0 = -0.5 * W * atn0, hw1 = -0.5 * W * atn1;
+        const double sg = g.sigma + gamma;
+        double phi[D], gx[D], gy[D];
+        eval_basis<P, DIFF>(x, y, bxe, A.lc, phi, gx, gy);
+        double Pr[RJ], Qr[RJ];
+#pragma unroll
+        for (int jj = 0; jj < RJ; ++jj) {
+            const int j = J0 + jj;
+            Pr[jj] = sgn * phi[j];
+            Qr[jj] = 0.0;
+            if (DIFF) {
+                if (gx_nz<P>(j) && gy_nz<P>(j)) Qr[jj] = -0.5 * (atn0 * gx[j] + atn1 * gy[j]);
+                else if (gx_nz<P>(j)) Qr[jj] = -0.5 * (atn0 * gx[j]);
+                else if (gy_nz<P>(j)) Qr[jj] = -0.5 * (atn1 * gy[j]);
+            }
+        }
+        const double Ws = OFF ? -(W * sgn) : W * sgn;
+        if (OFF) eval_basis<P, DIFF>(x, y, bxo, A.lc, phi, gx, gy);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const double Vc = Ws * phi[i];
+            double Uc = sg * Vc;
+            if (DIFF && gy_nz<P>(i)) Uc = fma(hw1, gy[i], Uc);
+            if (DIFF && gx_nz<P>(i)) Uc = fma(hw0, gx[i], Uc);
+#pragma unroll
+            for (int jj = 0; jj < RJ; ++jj) {
+                const int j = J0 + jj;
+                double v = acc[jj * D + i];
+                v = fma(Pr[jj], Uc, v);
+                if (DIFF && (gx_nz<P>(j) || gy_nz<P>(j))) v = fma(Qr[jj], Vc, v);
+                acc[jj * D + i] = v;
+            }
+        }
+    }
+}
+
+// one row part of one chunk of items of a giant element
+template <int P, int RS, int PART, bool DIFF, bool ADV>
+__device__ __forceinline__ void giant_part(const AsmArgs& A, double2* __restrict__ part, int lane, bool active, int nit, int f,
+                                           const FaceGeo& g, double sgn, bool down, const ElemBox& bxe, const ElemBox& bxo,
+                                           double* __restrict__ row0, int rowlen, int slot, int depth, int maxdepth,
+                                           double2& drun) {
+    using DM = Dm<P, RS>;
+    constexpr int D = DM::D, RJ = DM::RJ, NB = DM::NB, J0 = PART * RJ;
+    constexpr int NPQ = (NB + 1) / 2;
+    {
+        double acc[2 * NPQ];
+#pragma unroll
+        for (int v = 0; v < 2 * NPQ; ++v) acc[v] = 0.0;
+        if (active) giant_pass<P, RS, PART, DIFF, ADV, false>(A, f, g, sgn, down, bxe, bxe, acc);
+        __syncwarp();
+        if (active) {
+#pragma unroll
+            for (int kk = 0; kk < NPQ; ++kk) part[kk * kPartStride + lane] = make_double2(acc[2 * kk], acc[2 * kk + 1]);
+        }
+        __syncwarp();
+        if (lane < NPQ) {
+            for (int l = 0; l < nit; ++l) {         // faces in item order, after the volume sums
+                const double2 t = part[lane * kPartStride + l];
+                drun.x += t.x;
+                drun.y += t.y;
+            }
+        }
+    }
+    {
+        double acc[NB];
+#pragma unroll
+        for (int v = 0; v < NB; ++v) acc[v] = 0.0;
+        if (active) giant_pass<P, RS, PART, DIFF, ADV, true>(A, f, g, sgn, down, bxe, bxo, acc);
+        double* dst0 = row0 + slot * D;
+        if (active && depth == 0) {
+#pragma unroll
+            for (int jj = 0; jj < RJ; ++jj)
+#pragma unroll
+                for (int i = 0; i < D; ++i) dst0[(J0 + jj) * rowlen + i] = acc[jj * D + i];
+        }
+        for (int dd = 1; dd <= maxdepth; ++dd) {    // repeats of a neighbour add to its block, in item order
+            __threadfence_block();
+            __syncwarp();
+            if (active && depth == dd) {
+#pragma unroll
+                for (int jj = 0; jj < RJ; ++jj)
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        double* q = dst0 + (J0 + jj) * rowlen + i;
+                        *q = __ldcg(q) + acc[jj * D + i];
+                    }
+            }
+        }
+    }
+}
+
+template <int P, int RS, bool DIFF, bool ADV>
+__global__ void __launch_bounds__(kWarp) dg_face_giant_kernel(const __grid_constant__ AsmArgs A) {
+    using DM = Dm<P, RS>;
+    constexpr int D = DM::D, DD = DM::DD, NV = DM::NV, NB = DM::NB;
+    constexpr int NPQ = (NB + 1) / 2;
+    __shared__ double2 part[NPQ * kPartStride];
+    const int lane = threadIdx.x;
+    const int e_lane = A.elem_lo + blockIdx.x * kWarp + lane;
+    const bool big = e_lane < A.elem_hi && A.adj_off[e_lane + 1] - A.adj_off[e_lane] > kWarp;
+    unsigned todo = __ballot_sync(kFull, big);
+    unsigned zeros = 0;
+    while (todo) {
+        const int e = A.elem_lo + blockIdx.x * kWarp + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const int k0 = A.adj_off[e], k1 = A.adj_off[e + 1], g0 = A.grp_off[e];
+        const int rowlen = (A.grp_off[e + 1] - g0 + 1) * D;
+        double* row0 = A.data + (size_t)DD * ((size_t)g0 + e);
+        const int eg = gid_of(A, e);
+        const ElemBox bxe = A.ebox[e];
+        const int s0 = seg0_of(A, e), s1 = seg0_of(A, e + 1);
+        // running sums of the diagonal block (+ load): lane kk owns value pair kk of every part; volume segments first
+        double2 drun[RS];
+#pragma unroll
+        for (int part_i = 0; part_i < RS; ++part_i) {
+            drun[part_i] = make_double2(0.0, 0.0);
+            const int vi = part_i == 0 ? pair_dst<P, RS, 0>(lane) : pair_dst<P, RS, RS - 1>(lane);
+            if (lane < NPQ || (part_i == RS - 1 && vi < NV)) {
+                for (int s = s0; s < s1; ++s) {
+                    if (vi < NV) drun[part_i].x += A.vdiag[(size_t)s * NV + vi];
+                    if (vi + 1 < NV) drun[part_i].y += A.vdiag[(size_t)s * NV + vi + 1];
+                }
+            }
+        }
+        int heads_before = 0, dslot = 0;
+        for (int kc = k0; kc < k1; kc += kWarp) {
+            const int nit = min(kWarp, k1 - kc);
+            const bool active = lane < nit;
+            const int item = active ? A.adj_item[kc + lane] : 0;
+            const int nbr = active ? A.adj_nb[kc + lane] : 0;
+            const int f = (item & 0x7fffffff) >> 1;
+            const int side = item & 1;
+            const int og = active ? gid_of(A, nbr) : 0;
+            const bool headf = active && item >= 0;
+            const unsigned hm = __ballot_sync(kFull, headf);
+            const unsigned below = (2u << lane) - 1u;
+            const int slot = heads_before + __popc(hm & below) - 1 + (og > eg ? 1 : 0);
+            const int depth = active ? lane - (31 - __clz(hm & below)) : 0;      // a repeat of the previous chunk's neighbour: lane + 1
+            const int maxdepth = A.has_dups ? __reduce_max_sync(kFull, depth) : 0;
+            dslot += __popc(__ballot_sync(kFull, headf && og < eg));
+            heads_before += __popc(hm);
+            FaceGeo g;
+            ElemBox bxo = bxe;
+            double sgn = side ? -1.0 : 1.0;
+            bool down = false;
+            if (active) {
+                const FaceRec r = A.frec[f];
+                g.midx = r.midx; g.midy = r.midy; g.tanx = r.tanx; g.tany = r.tany; g.nx = r.nx; g.ny = r.ny; g.De = r.De;
+                g.sigma = A.fsigma ? A.fsigma[f] : r.sigma;
+                bxo = A.ebox[nbr];
+                down = A.c.if_upwind ? ((A.c.if_upwind[f] != 0) == (side == 1)) : false;
+            } else {
+                g.midx = g.midy = g.tanx = g.tany = g.nx = g.ny = g.De = g.sigma = 0.0;
+            }
+            giant_part<P, RS, 0, DIFF, ADV>(A, part, lane, active, nit, f, g, sgn, down, bxe, bxo, row0, rowlen, slot, depth, maxdepth,
+                                            drun[0]);
+            if (RS > 1)
+                giant_part<P, RS, RS - 1, DIFF, ADV>(A, part, lane, active, nit, f, g, sgn, down, bxe, bxo, row0, rowlen, slot, depth,
+                                                     maxdepth, drun[RS - 1]);
+            __syncwarp();
+        }
+        // diagonal block and load
+#pragma unroll
+        for (int part_i = 0; part_i < RS; ++part_i) {
+            const int vi = part_i == 0 ? pair_dst<P, RS, 0>(lane) : pair_dst<P, RS, RS - 1>(lane);
+            const bool mine = part_i == 0 ? (RS == 1 ? lane < NV / 2 : lane < NPQ) : (lane < NPQ + D / 2);
+            if (mine) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int v = vi + h;
+                    const double val = h ? drun[part_i].y : drun[part_i].x;
+                    if (v < DD) row0[(v / D) * rowlen + dslot * D + (v % D)] = val;
+                    else if (v < NV) A.load[(size_t)e * D + (v - DD)] = val;
+                }
+            }
+        }
+        // exact zeros of the finished rows (they were written by this warp: read them back past L1)
+        __threadfence_block();
+        __syncwarp();
+        for (int w = lane; w < D * rowlen; w += kWarp) zeros += (__ldcg(row0 + w) == 0.0);
+    }
+    if (zeros) atomicAdd(A.zero_count, (unsigned long long)zeros);
+}
+
+// =======================================================================================================================
 template <int P, int RS, bool DIFF, bool ADV>
 static int launch(const AsmArgs& A, cudaStream_t st) {
     using VS = VolSmem<P, RS, DIFF, ADV>;
@@ -936,6 +1165,10 @@ static int launch(const AsmArgs& A, cudaStream_t st) {
     const int blocks = (int)div_up(A.elem_hi - A.elem_lo, A.window);
     fk<<<blocks, kWarp, FS::TOTAL, st>>>(A);
     RB_LAUNCH_CHECK("dg_face_kernel");
+    if (A.has_giants) {
+        dg_face_giant_kernel<P, RS, DIFF, ADV><<<(int)div_up(A.elem_hi - A.elem_lo, kWarp), kWarp, 0, st>>>(A);
+        RB_LAUNCH_CHECK("dg_face_giant_kernel");
+    }
     return 0;
 }
 

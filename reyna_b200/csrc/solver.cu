@@ -573,7 +573,9 @@ extern "C" int reyna_b200_solve(int32_t n, int32_t n_ghost, int32_t d, int block
         if ((rc0 = launch_block_columns(n / d, d, indptr, indices, bcol_buf, st))) return rc0;
         s.bcol = bcol_buf;
     }
-    s.use_graphs = (halo == nullptr);
+    // multi-GPU: the application contains NCCL calls (halo exchanges, the coarse-level gather); capturing them is opt-in
+    // (REYNA_B200_DIST_GRAPHS=1) until it has been measured on every pool
+    s.use_graphs = (halo == nullptr) || (getenv("REYNA_B200_DIST_GRAPHS") && atoi(getenv("REYNA_B200_DIST_GRAPHS")) != 0);
     RB_LAUNCH_CHECK("block_jacobi_setup");
     if (opts->sweep_levels > 0 && opts->sweep_elems && opts->sweep_level_off && !mg && opts->method != 0) {
         // advection-reaction without diffusion: B is block triangular along the flow -> one sweep is (nearly) the solve.

@@ -355,18 +355,33 @@ def test_pipelined_download_equals_lazy_materialisation(rb, name, p, chunk):
         assert np.array_equal(np.asarray(dg.L.todense()), np.asarray(ref.L.todense()))
 
 
-def _fan_mesh(rb, n_spokes):
+def _fan_mesh(rb, n_spokes, double_edges=False):
     """One polygon with ``n_spokes`` + 3 vertices (a disc sector) surrounded by ``n_spokes`` thin neighbours: the centre element
-    has many interior faces and many sub-triangles (volume segments, rounds of its own)."""
+    has many interior faces and many sub-triangles (volume segments, rounds of its own).  ``double_edges``: every border between
+    the centre and a neighbour is a two-edge polyline, so every neighbour is repeated (merged blocks)."""
     th = np.linspace(0.0, 0.5 * np.pi, n_spokes + 1)
     inner = np.column_stack((0.5 * np.cos(th), 0.5 * np.sin(th)))
     outer = np.column_stack((np.cos(th), np.sin(th)))
     v = np.vstack(([[0.0, 0.0]], inner, outer))
     ni = n_spokes + 1
-    regions = [np.concatenate(([0], 1 + np.arange(ni)))]
     pts = [[0.2, 0.2]]
+    if not double_edges:
+        regions = [np.concatenate(([0], 1 + np.arange(ni)))]
+        for k in range(n_spokes):
+            regions.append(np.array([1 + k, 1 + ni + k, 1 + ni + k + 1, 1 + k + 1]))
+            pts.append(list(0.25 * (inner[k] + inner[k + 1] + outer[k] + outer[k + 1])))
+        return rb.PolyMesh(v, regions, np.array(pts), None)
+    thm = 0.5 * (th[:-1] + th[1:])
+    mid = np.column_stack((0.53 * np.cos(thm), 0.53 * np.sin(thm)))          # kink of every border (not collinear)
+    v = np.vstack((v, mid))
+    m0 = 1 + 2 * ni
+    centre = [0]
     for k in range(n_spokes):
-        regions.append(np.array([1 + k, 1 + ni + k, 1 + ni + k + 1, 1 + k + 1]))
+        centre += [1 + k, m0 + k]
+    centre.append(1 + n_spokes)
+    regions = [np.array(centre)]
+    for k in range(n_spokes):
+        regions.append(np.array([1 + k, 1 + ni + k, 1 + ni + k + 1, 1 + k + 1, m0 + k]))
         pts.append(list(0.25 * (inner[k] + inner[k + 1] + outer[k] + outer[k + 1])))
     return rb.PolyMesh(v, regions, np.array(pts), None)
 
@@ -419,40 +434,38 @@ def test_element_with_more_than_32_triangles_uses_segments(rb):
     assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
 
 
-def test_element_with_more_than_32_faces_is_rejected(rb):
-    geo = rb.DGFEMGeometry(_fan_mesh(rb, 40))
+@pytest.mark.parametrize("n_spokes,name,p", [(40, "variable", 2), (60, "adr", 1), (45, "variable", 3), (50, "variable_hyperbolic", 2)])
+def test_element_with_33_to_64_faces_takes_the_giant_path(rb, n_spokes, name, p):
+    """More than 32 (element, face) items in one element (many-sided / agglomerated polygons): dg_face_giant_kernel assembles
+    its block row (and its > 32 sub-triangles go through volume segments); the neighbours stay on the fast path."""
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(_fan_mesh(rb, n_spokes))
+    dg = _run(rb, geo, name, p, solve=False)
+    B, L, info = dg_oracle.assemble(geo, p, **PROBLEMS[name]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
+
+
+@pytest.mark.parametrize("n_spokes,name,p", [(20, "variable", 2), (12, "adr", 3), (25, "variable_hyperbolic", 1)])
+def test_giant_element_with_repeated_neighbours(rb, n_spokes, name, p):
+    """2 * n_spokes items in the centre element, every neighbour twice: merged blocks inside and across the 32-item chunks."""
+    from oracle import dg_oracle
+    geo = rb.DGFEMGeometry(_fan_mesh(rb, n_spokes, double_edges=True))
+    dg = _run(rb, geo, name, p, solve=False)
+    assert dg._dev["structure"]["n_dup_items"] > 0
+    B, L, info = dg_oracle.assemble(geo, p, **PROBLEMS[name]["data"])
+    max_rel, bad, noise = util.compare_csr(dg.B, B, info.dim_elem)
+    assert bad == 0 and max_rel <= util.TOL_ENTRY
+    assert util.rel_inf(np.asarray(dg.L.todense()), np.asarray(L.todense())) <= util.TOL_ENTRY
+
+
+def test_element_with_more_than_64_faces_is_rejected(rb):
+    geo = rb.DGFEMGeometry(_fan_mesh(rb, 70))
     dg = rb.DGFEM(geo, polynomial_degree=1)
     dg.add_data(**PROBLEMS["adr"]["data"])
     with pytest.raises(rb.ReynaB200Error):
         dg.dgfem(solve=False)
-
-
-def test_plot_data_matches_the_reference_recipe(rb):
-    """plot_DG's data preparation (tools.py:15-114) batched on the device: vertex values, face colours and limits equal the
-    per-element recipe of the reference evaluated with the oracle basis."""
-    from oracle import dg_oracle
-    z, geo = util.load_golden("square64")
-    key = [str(c) for c in z["cases"] if str(c).endswith("_p2")][0]
-    name, p = util.split_case(key)
-    sol = z[key + "_solution"]
-    d = rb.plot_data(sol, geo, p)
-    orders = dg_oracle.basis_orders(p)
-    dim = orders.shape[0]
-    bb = np.asarray(geo.elem_bounding_boxes, dtype=float)
-    vals, means = [], []
-    for t in range(geo.n_elements):
-        node = geo.nodes[np.asarray(geo.mesh.filtered_regions[t])]
-        phi, _ = dg_oracle.basis_and_grad(node, np.repeat(bb[t][None], node.shape[0], axis=0), orders, need_grad=False)
-        u = sol[t * dim:(t + 1) * dim] @ phi                    # phi: (d, M)
-        vals.append(u)
-        means.append(u.mean())
-    u = np.concatenate(vals)
-    assert np.allclose(d["xyz"][:, 2], u, rtol=0, atol=1e-12 * np.abs(u).max())
-    s = max(abs(u.max()), abs(u.min()))
-    c = np.abs(np.array(means) / s)
-    assert np.allclose(d["facecolor"], np.column_stack((c, c, 1 - c)), atol=1e-12)
-    assert np.allclose(d["zlim"], (u.min(), u.max()), atol=1e-12 * s)
-    assert d["offsets"][-1] == d["xyz"].shape[0] and d["offsets"].shape[0] == geo.n_elements + 1
 
 
 @pytest.mark.parametrize("n_cells,name,p", [(1, "adr", 2), (1, "hyperbolic", 1), (3, "variable", 3), (4, "adr", 1)])

@@ -172,6 +172,17 @@ int reyna_b200_assemble_range(const rb_geom *g, const rb_structure *s, const rb_
                               double sigma_D, double *data, double *load, long long *zero_count, void *workspace,
                               size_t workspace_bytes, int32_t elem_lo, int32_t elem_hi, int32_t vround_lo,
                               int32_t vround_hi, void *stream);
+/* The two halves of reyna_b200_assemble_range.  The volume kernel reads neither the adjacency nor the CSR layout: it may
+ * run while reyna_b200_structure_known / reyna_b200_csr_pattern still work on another stream; the face half needs both
+ * (and the volume sums) and is launched after them. */
+int reyna_b200_assemble_volume_range(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
+                                     double sigma_D, double *data, double *load, long long *zero_count, void *workspace,
+                                     size_t workspace_bytes, int32_t elem_lo, int32_t elem_hi, int32_t vround_lo,
+                                     int32_t vround_hi, void *stream);
+int reyna_b200_assemble_faces_range(const rb_geom *g, const rb_structure *s, const rb_coefs *c, const rb_quad *q,
+                                    double sigma_D, double *data, double *load, long long *zero_count, void *workspace,
+                                    size_t workspace_bytes, int32_t elem_lo, int32_t elem_hi, int32_t vround_lo,
+                                    int32_t vround_hi, void *stream);
 
 /* Boundary faces: elliptic (Dirichlet SIPG) and inflow terms subtracted in place from the diagonal blocks and the
  * load (replaces _diffusion_bcs_contribution / _advection_bcs_contribution, main.py:376-474, and

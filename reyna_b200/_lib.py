@@ -20,6 +20,7 @@ EXPORTS = (
     "reyna_b200_nccl_unique_id", "reyna_b200_comm_create", "reyna_b200_comm_destroy", "reyna_b200_dist_create", "reyna_b200_dist_destroy", "reyna_b200_dist_counters",
     "reyna_b200_nccl_halo", "reyna_b200_nccl_allreduce",
     "reyna_b200_geometry_tables_bytes", "reyna_b200_geometry_tables", "reyna_b200_assemble_workspace", "reyna_b200_assemble", "reyna_b200_assemble_prepare", "reyna_b200_assemble_range",
+    "reyna_b200_assemble_volume_range", "reyna_b200_assemble_faces_range",
     "reyna_b200_boundary", "reyna_b200_compact_workspace", "reyna_b200_compact_count", "reyna_b200_compact_fill",
     "reyna_b200_mg_create", "reyna_b200_mg_destroy", "reyna_b200_mg_info", "reyna_b200_mg_apply",
     "reyna_b200_solve_workspace", "reyna_b200_solve", "reyna_b200_spmv", "reyna_b200_errors_workspace",
@@ -148,6 +149,9 @@ def lib() -> C.CDLL:
     L.reyna_b200_assemble_range.restype = C.c_int
     L.reyna_b200_assemble_range.argtypes = [C.POINTER(RbGeom), C.POINTER(RbStructure), C.POINTER(RbCoefs), C.POINTER(RbQuad),
                                             C.c_double, vp, vp, i64p, vp, C.c_size_t, i32, i32, i32, i32, vp]
+    for fn in (L.reyna_b200_assemble_volume_range, L.reyna_b200_assemble_faces_range):
+        fn.restype = C.c_int
+        fn.argtypes = L.reyna_b200_assemble_range.argtypes
     L.reyna_b200_assemble_workspace.restype = C.c_size_t
     L.reyna_b200_assemble_workspace.argtypes = [i32, i32, i32, i32]
     L.reyna_b200_boundary.restype = C.c_int

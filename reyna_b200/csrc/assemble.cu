@@ -241,7 +241,7 @@ static int run_prepare(const AsmArgs& A, bool diff, cudaStream_t st) {
 }
 
 static int run_range(AsmArgs& A, const rb_structure* s, int p, bool diff, bool adv, int elem_lo, int elem_hi, int vround_lo,
-                     int vround_hi, cudaStream_t st) {
+                     int vround_hi, cudaStream_t st, int phases = 3) {
     const rb_geom& g = A.g;
     RB_REQUIRE(A.data && A.load && A.zero_count, RB_E_ARG, "reyna_b200_assemble: null output");
     RB_REQUIRE(0 <= elem_lo && elem_lo <= elem_hi && elem_hi <= g.n_rows && 0 <= vround_lo && vround_lo <= vround_hi &&
@@ -254,7 +254,8 @@ static int run_range(AsmArgs& A, const rb_structure* s, int p, bool diff, bool a
                "reyna_b200_assemble: the geometry carries no volume stream (rb_geom.tri_xy / vround_tri0)");
     RB_REQUIRE((g.tri_seg == nullptr) == (g.elem_seg0 == nullptr), RB_E_ARG,
                "reyna_b200_assemble: tri_seg and elem_seg0 must be given together");
-    RB_REQUIRE(s->max_items <= 64, RB_E_ARG, "reyna_b200_assemble: an element has more than 64 contributing interior faces");
+    RB_REQUIRE(!(phases & 2) || s->max_items <= 64, RB_E_ARG,
+               "reyna_b200_assemble: an element has more than 64 contributing interior faces");
     RB_REQUIRE(((uintptr_t)A.data & 15) == 0 && ((uintptr_t)A.load & 7) == 0, RB_E_ARG,
                "reyna_b200_assemble: data must be 16-byte aligned");
     const rb_coefs& c = A.c;
@@ -266,7 +267,7 @@ static int run_range(AsmArgs& A, const rb_structure* s, int p, bool diff, bool a
     A.elem_hi = elem_hi;
     A.vround_lo = vround_lo;
     A.vround_hi = vround_hi;
-    return launch_assemble_items(A, p, diff, adv, st);
+    return launch_assemble_items(A, p, diff, adv, st, phases);
 }
 
 extern "C" int reyna_b200_assemble(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
@@ -306,4 +307,33 @@ extern "C" int reyna_b200_assemble_range(const rb_geom* g, const rb_structure* s
                        adv);
     if (rc) return rc;
     return run_range(A, s, q->p, diff, adv, elem_lo, elem_hi, vround_lo, vround_hi, (cudaStream_t)stream);
+}
+
+// The two halves of reyna_b200_assemble_range: the volume kernel needs neither the adjacency nor the CSR layout, so a caller
+// may run it while reyna_b200_structure_known / reyna_b200_csr_pattern are still working on another stream, and launch the
+// face kernel (which needs both, and the volume sums) afterwards.
+extern "C" int reyna_b200_assemble_volume_range(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
+                                                double sigma_D, double* data, double* load, long long* zero_count, void* workspace,
+                                                size_t workspace_bytes, int32_t elem_lo, int32_t elem_hi, int32_t vround_lo,
+                                                int32_t vround_hi, void* stream) {
+    RB_REQUIRE(data && load && zero_count, RB_E_ARG, "reyna_b200_assemble_volume_range: null argument");
+    AsmArgs A;
+    bool diff, adv;
+    int rc = make_args("reyna_b200_assemble_volume_range", g, s, c, q, sigma_D, data, load, zero_count, workspace, workspace_bytes, A,
+                       diff, adv);
+    if (rc) return rc;
+    return run_range(A, s, q->p, diff, adv, elem_lo, elem_hi, vround_lo, vround_hi, (cudaStream_t)stream, 1);
+}
+
+extern "C" int reyna_b200_assemble_faces_range(const rb_geom* g, const rb_structure* s, const rb_coefs* c, const rb_quad* q,
+                                               double sigma_D, double* data, double* load, long long* zero_count, void* workspace,
+                                               size_t workspace_bytes, int32_t elem_lo, int32_t elem_hi, int32_t vround_lo,
+                                               int32_t vround_hi, void* stream) {
+    RB_REQUIRE(data && load && zero_count, RB_E_ARG, "reyna_b200_assemble_faces_range: null argument");
+    AsmArgs A;
+    bool diff, adv;
+    int rc = make_args("reyna_b200_assemble_faces_range", g, s, c, q, sigma_D, data, load, zero_count, workspace, workspace_bytes, A,
+                       diff, adv);
+    if (rc) return rc;
+    return run_range(A, s, q->p, diff, adv, elem_lo, elem_hi, vround_lo, vround_hi, (cudaStream_t)stream, 2);
 }

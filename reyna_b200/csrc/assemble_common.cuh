@@ -43,7 +43,8 @@ struct AsmArgs {
 };
 
 // item-per-lane kernels (assemble_items.cu)
-int launch_assemble_items(const AsmArgs& A, int p, bool diff, bool adv, cudaStream_t st);
+// phases: bit 0 = volume kernel, bit 1 = face kernel(s)
+int launch_assemble_items(const AsmArgs& A, int p, bool diff, bool adv, cudaStream_t st, int phases);
 int items_max_face_items();
 int items_max_segments();
 

@@ -1149,19 +1149,20 @@ __global__ void __launch_bounds__(kWarp) dg_face_giant_kernel(const __grid_const
 
 // =======================================================================================================================
 template <int P, int RS, bool DIFF, bool ADV>
-static int launch(const AsmArgs& A, cudaStream_t st) {
+static int launch(const AsmArgs& A, cudaStream_t st, int phases) {
     using VS = VolSmem<P, RS, DIFF, ADV>;
     using FS = FaceSmem<P, RS, DIFF, ADV>;
     auto vk = dg_volume_kernel<P, RS, DIFF, ADV>;
     auto fk = dg_face_kernel<P, RS, DIFF, ADV>;
     RB_CUDA(cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS::TOTAL));
     RB_CUDA(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS::TOTAL));
-    if (A.vround_hi > A.vround_lo) {
+    if ((phases & 1) && A.vround_hi > A.vround_lo) {
         const int nrounds = A.vround_hi - A.vround_lo;
         RB_CUDA(cudaMemsetAsync(A.vol_next, 0, sizeof(int), st));
         vk<<<nrounds < kVolWarps ? nrounds : kVolWarps, kWarp, VS::TOTAL, st>>>(A);
         RB_LAUNCH_CHECK("dg_volume_kernel");
     }
+    if (!(phases & 2)) return 0;
     const int blocks = (int)div_up(A.elem_hi - A.elem_lo, A.window);
     fk<<<blocks, kWarp, FS::TOTAL, st>>>(A);
     RB_LAUNCH_CHECK("dg_face_kernel");
@@ -1173,10 +1174,10 @@ static int launch(const AsmArgs& A, cudaStream_t st) {
 }
 
 template <int P, int RS>
-static int dispatch(const AsmArgs& A, bool diff, bool adv, cudaStream_t st) {
-    if (diff && adv) return launch<P, RS, true, true>(A, st);
-    if (diff) return launch<P, RS, true, false>(A, st);
-    return launch<P, RS, false, true>(A, st);
+static int dispatch(const AsmArgs& A, bool diff, bool adv, cudaStream_t st, int phases) {
+    if (diff && adv) return launch<P, RS, true, true>(A, st, phases);
+    if (diff) return launch<P, RS, true, false>(A, st, phases);
+    return launch<P, RS, false, true>(A, st, phases);
 }
 
 }  // namespace items
@@ -1184,7 +1185,7 @@ static int dispatch(const AsmArgs& A, bool diff, bool adv, cudaStream_t st) {
 int items_max_face_items() { return items::kWarp; }
 int items_max_segments() { return items::kMaxSeg; }
 
-int launch_assemble_items(const AsmArgs& A0, int p, bool diff, bool adv, cudaStream_t st) {
+int launch_assemble_items(const AsmArgs& A0, int p, bool diff, bool adv, cudaStream_t st, int phases) {
     // elements per face CTA: at least ~6 waves of CTAs on the GPU (8 one-warp CTAs per SM) so that the last wave does not
     // dominate small partitions, 16..64 elements
     AsmArgs A = A0;
@@ -1193,9 +1194,9 @@ int launch_assemble_items(const AsmArgs& A0, int p, bool diff, bool adv, cudaStr
     while (w > 16 && (int64_t)n < (int64_t)w * 6 * 8 * kNumSMs) w >>= 1;
     A.window = w;
     switch (p) {
-        case 1: return items::dispatch<1, 1>(A, diff, adv, st);
-        case 2: return items::dispatch<2, 1>(A, diff, adv, st);
-        default: return items::dispatch<3, 2>(A, diff, adv, st);
+        case 1: return items::dispatch<1, 1>(A, diff, adv, st, phases);
+        case 2: return items::dispatch<2, 1>(A, diff, adv, st, phases);
+        default: return items::dispatch<3, 2>(A, diff, adv, st, phases);
     }
 }
 

@@ -484,10 +484,20 @@ class DGFEM:
         # are known on the host and the call does not have to synchronise to return them
         known = getattr(self._geo, '_rb_counts', None) if has_diff else None
         key = (R, int(fg.n_iface))
+        main_stream = torch.cuda.current_stream()
+        side = self._stream(torch, dev, 'pattern')
+        structure_ready = None
         if known is not None and known[0] == key:
+            # the counters are known: adjacency + index pattern are built on the side stream while the main stream already runs
+            # the penalties prepass and the volume kernel (neither needs the structure); the face kernel waits for the event
             st.n_items, st.n_groups, st.n_dup_items, st.max_items = known[1]
-            _lib.check(L.reyna_b200_structure_known(C.byref(g), 1, None, C.byref(st), _ptr(ws), ws_bytes, sp),
-                       'reyna_b200_structure_known')
+            side.wait_stream(main_stream)
+            _lib.check(L.reyna_b200_structure_known(C.byref(g), 1, None, C.byref(st), _ptr(ws), ws_bytes,
+                                                    C.c_void_p(side.cuda_stream)), 'reyna_b200_structure_known')
+            structure_ready = torch.cuda.Event()
+            structure_ready.record(side)
+            for t in (adj_off, adj_item, adj_nb, grp_off, counts, ws):
+                t.record_stream(side)
         else:
             _lib.check(L.reyna_b200_structure(C.byref(g), int(has_diff), _ptr(cd.get('if_upwind')), C.byref(st), _ptr(ws),
                                               ws_bytes, sp), 'reyna_b200_structure')
@@ -496,6 +506,7 @@ class DGFEM:
                     self._geo._rb_counts = (key, (st.n_items, st.n_groups, st.n_dup_items, st.max_items))
                 except Exception:   # pragma: no cover - exotic geometry objects
                     pass
+            side.wait_stream(main_stream)
         nnz = d * d * (R + st.n_groups)
         if nnz >= 2 ** 31:
             raise _lib.ReynaB200Error(f'nnz = {nnz} does not fit the int32 CSR indices')
@@ -505,11 +516,10 @@ class DGFEM:
         data = torch.empty(nnz, **f64)
         load = torch.empty(N, **f64)
         zero_count = torch.zeros(1, dtype=torch.int64, device=dev)
-        # the index arrays only depend on the structure: they are written on a side stream while the assembly runs, and joined
+        # the index arrays only depend on the structure: they are written on the side stream while the assembly runs, and joined
         # before the step ends
-        main_stream = torch.cuda.current_stream()
-        side = self._stream(torch, dev, 'pattern')
-        side.wait_stream(main_stream)
+        if structure_ready is not None:
+            side.wait_stream(main_stream)            # (allocations above)
         _lib.check(L.reyna_b200_csr_pattern(C.byref(g), C.byref(st), p, _ptr(indptr), _ptr(indices),
                                             C.c_void_p(side.cuda_stream)), 'reyna_b200_csr_pattern')
         indptr.record_stream(side)
@@ -518,6 +528,7 @@ class DGFEM:
         aws = torch.empty(aws_bytes, dtype=torch.uint8, device=dev)
         return dict(g=g, st=st, co=co, q=q, R=R, N=N, d=d, nnz=int(nnz), indptr=indptr, indices=indices, data=data, load=load,
                     zero_count=zero_count, aws=aws, aws_bytes=aws_bytes, side=side, main=main_stream, dev=dev, prepared=False,
+                    structure_ready=structure_ready,
                     structure=dict(adj_off=adj_off, adj_item=adj_item, adj_nb=adj_nb, grp_off=grp_off, n_items=st.n_items,
                                    n_groups=st.n_groups, n_dup_items=st.n_dup_items), spill=None, _keep=(ws, counts))
 
@@ -528,10 +539,16 @@ class DGFEM:
             _lib.check(L.reyna_b200_assemble_prepare(C.byref(g), C.byref(st), C.byref(co), C.byref(q), float(self.sigma_D),
                                                      _ptr(ctx['aws']), ctx['aws_bytes'], sp), 'reyna_b200_assemble_prepare')
             ctx['prepared'] = True
-        _lib.check(L.reyna_b200_assemble_range(C.byref(g), C.byref(st), C.byref(co), C.byref(q), float(self.sigma_D),
-                                               _ptr(ctx['data']), _ptr(ctx['load']), _ptr(ctx['zero_count']), _ptr(ctx['aws']),
-                                               ctx['aws_bytes'], int(e_lo), int(e_hi), int(r_lo), int(r_hi), sp),
-                   'reyna_b200_assemble_range')
+        args = (C.byref(g), C.byref(st), C.byref(co), C.byref(q), float(self.sigma_D), _ptr(ctx['data']), _ptr(ctx['load']),
+                _ptr(ctx['zero_count']), _ptr(ctx['aws']), ctx['aws_bytes'], int(e_lo), int(e_hi), int(r_lo), int(r_hi), sp)
+        if ctx['structure_ready'] is not None:
+            # the structure is still being built on the side stream: volume kernel first, the face kernel after the join
+            _lib.check(L.reyna_b200_assemble_volume_range(*args), 'reyna_b200_assemble_volume_range')
+            ctx['main'].wait_event(ctx['structure_ready'])
+            ctx['structure_ready'] = None
+            _lib.check(L.reyna_b200_assemble_faces_range(*args), 'reyna_b200_assemble_faces_range')
+        else:
+            _lib.check(L.reyna_b200_assemble_range(*args), 'reyna_b200_assemble_range')
         be = bd['bnd_elem_host']
         n_all = int(be.shape[0])
         if n_all:

@@ -252,6 +252,9 @@ typedef struct {
                                 * the levels below P1 are AGGLOMERATED P1 spaces: groups of 4 consecutive elements,
                                 * linear polynomials on the bounding box of the group, 3 x 3 block Jacobi smoothing --
                                 * instead of the piecewise-constant aggregation chain                          */
+    int32_t fp32_levels;       /* != 0: the smoothing sweeps of the agglomerated-P1 levels read a single-precision copy of the
+                                * level matrices (half the traffic of the sweeps; vectors, residuals and the Krylov iteration
+                                * stay in double precision)                                                            */
 } rb_mg_opts;
 /* Distributed hierarchy (dd != NULL): the fine and P1 levels are the rank's rows in LOCAL column numbering (halo exchange
  * through dd->dist), the piecewise-constant level is GLOBAL: the caller gathers every rank's P0 rows (global element

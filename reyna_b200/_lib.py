@@ -58,7 +58,8 @@ class RbStructure(C.Structure):
 
 
 class RbMgOpts(C.Structure):
-    _fields_ = [("nu", C.c_int32), ("omega", C.c_double), ("alpha", C.c_double), ("elem_bbox", C.c_void_p)]
+    _fields_ = [("nu", C.c_int32), ("omega", C.c_double), ("alpha", C.c_double), ("elem_bbox", C.c_void_p),
+                ("fp32_levels", C.c_int32)]
 
 
 class RbMgDist(C.Structure):

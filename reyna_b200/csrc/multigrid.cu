@@ -41,6 +41,7 @@ struct MgLevel {
     double* minv = nullptr;      // [n_blk][3][3]  omega * inverse of the diagonal block
     double* bbox = nullptr;      // [n_blk][4]     bounding box of the (agglomerated) element
     double* tr = nullptr;        // [n_blk][8]     its P1 basis expressed in the basis of its aggregate (next level)
+    float* dataf = nullptr;      // [nnz] single-precision copy of `data` for the smoothing sweeps (rb_mg_opts.fp32_levels)
 };
 
 }  // namespace rb
@@ -603,9 +604,9 @@ static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
 // every x value is gathered once and used for the three rows.  SWEEP == false: out = b - A x;  SWEEP == true: the damped block
 // Jacobi update out = x + Minv (b - A x) (omega folded into minv), written to another buffer than x.  Columns >= ncols are
 // ghost couplings the level ignores.  Fixed shuffle tree: deterministic.
-template <bool SWEEP>
+template <bool SWEEP, typename T>
 __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols, const int32_t* __restrict__ indptr,
-                                                            const int32_t* __restrict__ indices, const double* __restrict__ data,
+                                                            const int32_t* __restrict__ indices, const T* __restrict__ data,
                                                             const double* __restrict__ minv, const double* __restrict__ b,
                                                             const double* __restrict__ x, double* __restrict__ out) {
     const int lane = threadIdx.x & 7;
@@ -619,9 +620,9 @@ __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols
             const int c = indices[lo + j];
             if (c < ncols) {
                 const double xv = x[c];
-                s0 = fma(data[lo + j], xv, s0);
-                s1 = fma(data[lo + len + j], xv, s1);
-                s2 = fma(data[lo + 2 * len + j], xv, s2);
+                s0 = fma((double)data[lo + j], xv, s0);
+                s1 = fma((double)data[lo + len + j], xv, s1);
+                s2 = fma((double)data[lo + 2 * len + j], xv, s2);
             }
         }
 #pragma unroll
@@ -640,6 +641,10 @@ __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols
             }
         }
     }
+}
+
+__global__ void mgb_to_float(int64_t n, const double* __restrict__ in, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
 }
 
 // V-cycle on the agglomerated-P1 chain, level k: blev[k].b holds the right-hand side, the result is left in blev[k].x.
@@ -661,7 +666,8 @@ static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     mg_block_apply<false><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.b, cur);
     auto sweep = [&]() {
         if (dist0 && !rc) rc = dist_halo_d(mg->dist, cur, 3, st);
-        mgb_block_row<true><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth);
+        if (L.dataf) mgb_block_row<true, float><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.dataf, L.minv, L.b, cur, oth);
+        else mgb_block_row<true, double><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth);
         double* t = cur; cur = oth; oth = t;
     };
     for (int s = 1; s < mg->nu; ++s) sweep();
@@ -669,7 +675,8 @@ static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     MgLevel& C = mg->blev[k + 1];
     if (dist0 && !rc) rc = dist_halo_d(mg->dist, cur, 3, st);
     if (rc) return rc;
-    mgb_block_row<false><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth);
+    if (L.dataf) mgb_block_row<false, float><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.dataf, L.minv, L.b, cur, oth);
+    else mgb_block_row<false, double><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth);
     if (dist0) {
         // this rank's aggregates -> slice of the global level-1 right-hand side, all-gathered; the chain below is replicated
         const int nagg_loc = (L.n_blk + 3) / 4;
@@ -953,6 +960,16 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
         }
         mg->nblev = k + 1;
         mg->nlev = mg->nblev;
+        if (opts && opts->fp32_levels) {
+            // the smoothing sweeps are bound by the matrix values: a single-precision copy halves their traffic (the hierarchy is
+            // a preconditioner; the Krylov iteration and every residual stay in double precision)
+            for (int q = 0; q + 1 < mg->nblev; ++q) {
+                MgLevel& Lq = mg->blev[q];
+                if ((rc = dev_alloc(mg, (void**)&Lq.dataf, sizeof(float) * (size_t)Lq.nnz))) return fail(rc);
+                mgb_to_float<<<mg_grid(Lq.nnz), kMgThreads, 0, st>>>(Lq.nnz, Lq.data, Lq.dataf);
+            }
+            RB_LAUNCH_CHECK("mgb_to_float");
+        }
         for (int q = 0; q < mg->nblev; ++q) { mg->lev[q].n = mg->blev[q].n; mg->lev[q].nnz = mg->blev[q].nnz; }   // reyna_b200_mg_info
         MgLevel& Lc = mg->blev[mg->nblev - 1];
         double* scratch_a = nullptr;

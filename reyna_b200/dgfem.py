@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import time
+import os
 import typing
 import warnings
 
@@ -73,6 +74,8 @@ class DGFEM:
         # ('sweep'; 'bj' = plain block Jacobi)
         # 'mg_hierarchy': 'agglomerated' (P1 spaces on groups of 4 elements; defaults mg_nu 2, mg_omega 0.8, mg_alpha 2.2) or
         # 'aggregation' (piecewise constants; defaults 3, 0.7, 1.8) -- set 'mg_nu' / 'mg_omega' / 'mg_alpha' to override
+        # 'mg_fp32': True = the smoothing sweeps read single-precision copies of the level matrices (measured: same solve time at
+        # config 5, the sweeps are bound by the gathers of x, not by the matrix values -- off by default)
         # 'rtol' is below the rounding floor on purpose: like spsolve, the iteration runs until the TRUE residual stops improving;
         # at or below 'accept_rtol' that floor counts as convergence, above it the solve warns (solve_info['converged'] False)
         self.solver_options = {'method': 'auto', 'rtol': 1e-14, 'accept_rtol': 1e-7, 'max_iter': 200000, 'check_every': 10,
@@ -728,7 +731,8 @@ class DGFEM:
                     mo = _lib.RbMgOpts(nu=int(so.get('mg_nu', 2 if agglo else 3)),
                                        omega=float(so.get('mg_omega', 0.8 if agglo else 0.7)),
                                        alpha=float(so.get('mg_alpha', 2.2 if agglo else 1.8)),
-                                       elem_bbox=_ptr(dv['bbox']) if agglo else None)
+                                       elem_bbox=_ptr(dv['bbox']) if agglo else None,
+                                       fp32_levels=int(bool(so.get('mg_fp32', os.environ.get('REYNA_B200_MG_FP32', '0') != '0'))))
                     _lib.check(L.reyna_b200_mg_create(N, d, self.polydegree, _ptr(s_indptr), _ptr(s_indices), _ptr(s_data),
                                                       C.byref(mo), None, C.byref(mg), sp), 'reyna_b200_mg_create')
                     nl = C.c_int32(0)

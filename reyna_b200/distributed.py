@@ -203,7 +203,8 @@ class DistributedDGFEM:
                     agglo = so.get("mg_hierarchy", "agglomerated") == "agglomerated"
                     mo = _lib.RbMgOpts(nu=int(so.get("mg_nu", 2 if agglo else 3)),
                                        omega=float(so.get("mg_omega", 0.8 if agglo else 0.7)),
-                                       alpha=float(so.get("mg_alpha", 2.2 if agglo else 1.8)))
+                                       alpha=float(so.get("mg_alpha", 2.2 if agglo else 1.8)),
+                                       fp32_levels=int(bool(so.get("mg_fp32", os.environ.get("REYNA_B200_MG_FP32", "0") != "0"))))
                     bounds32 = (C.c_int32 * (self.world + 1))(*[int(b) for b in self.bounds])
                     dd = _lib.RbMgDist(dist=ctx["handle"], rank=self.rank, world=self.world,
                                        n_ghost_elem=fg.n_elem - fg.n_rows, n_global_elem=int(self.bounds[-1]),

@@ -142,6 +142,24 @@ def test_multigrid_solution_matches_spsolve(rb):
         assert util.rel_l2(dg.solution, x) <= util.TOL_SOLUTION, dg.solve_info
 
 
+@pytest.mark.parametrize("name,p", [("adr", 2), ("diffusion", 1)])
+def test_single_precision_level_matrices_only_change_the_preconditioner(rb, name, p):
+    """rb_mg_opts.fp32_levels: the smoothing sweeps read float copies of the level matrices; the Krylov iteration, its
+    residuals and the stopping rule stay in double precision, so the solution agrees to the solve tolerance and the iteration
+    count moves by a few at most."""
+    geo = rb.DGFEMGeometry(rb.tiled_voronoi_mesh(16384, tiles=4, seed=7), subtriangulation="fan")
+    out = {}
+    for fp32 in (False, True):
+        dg = rb.DGFEM(geo, polynomial_degree=p)
+        dg.add_data(**PROBLEMS[name]["data"])
+        dg.solver_options.update(rtol=1e-9, mg_fp32=fp32)
+        dg.dgfem(solve=True)
+        assert dg.solve_info["converged"], dg.solve_info
+        out[fp32] = (dg.solution.copy(), dg.solve_info["iterations"])
+    assert util.rel_l2(out[True][0], out[False][0]) <= 1e-7
+    assert out[True][1] <= out[False][1] * 1.15 + 4, (out[True][1], out[False][1])
+
+
 def test_block_jacobi_still_available(rb):
     geo = rb.DGFEMGeometry(rb.voronoi_mesh(2000, seed=2), subtriangulation="fan")
     dg = rb.DGFEM(geo, polynomial_degree=2)

@@ -416,6 +416,13 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     pb.record()
     torch.cuda.synchronize()
     fp64_peak_tflops = fl.value / (pa.elapsed_time(pb) * 1e-3) / 1e12
+    # FP64 tensor-core (DMMA m8n8k4) rate beside it: the A/B that decides whether the 6x6 contractions belong on tensor cores
+    L.reyna_b200_dmma_probe(4000, scratch.data_ptr(), C.byref(fl), sp)
+    pa.record()
+    L.reyna_b200_dmma_probe(4000, scratch.data_ptr(), C.byref(fl), sp)
+    pb.record()
+    torch.cuda.synchronize()
+    dmma_peak_tflops = fl.value / (pa.elapsed_time(pb) * 1e-3) / 1e12
 
     if not args.no_solve:
         # the second half of BASELINE.json's metric: dgfem(solve=True) wall time on the same workload (host callables,
@@ -495,7 +502,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": alg_bytes, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                      "fp64": {"algorithmic_tflop": alg_flops / 1e12, "achieved_tflops": alg_flops / (k_ms * 1e-3) / 1e12,
-                              "fma_probe_peak_tflops": fp64_peak_tflops}},
+                              "fma_probe_peak_tflops": fp64_peak_tflops,
+                                       "dmma_probe_peak_tflops": dmma_peak_tflops}},
     }
     if solve_line is not None:
         line["solve"] = solve_line

@@ -351,6 +351,9 @@ int reyna_b200_evaluate(int p, int32_t n_points, const double *bbox, const doubl
 /* FP64 FMA micro-benchmark used as the compute roofline denominator: runs `iters` dependent-chain FMAs on every
  * lane of a full grid and returns the flop count through *flops (host). */
 int reyna_b200_fma_probe(int iters, double *scratch_dev, double *flops, void *stream);
+/* The same for the FP64 tensor-core path (mma.sync m8n8k4 f64, 8 independent accumulator tiles per warp): the measured DMMA
+ * rate that DESIGN.md section 4 weighs against the 6x6 blocks of the assembly (an 8x8 tile is 56 % full). */
+int reyna_b200_dmma_probe(int iters, double *scratch_dev, double *flops, void *stream);
 
 /* Number of CUDA kernels this library has launched in the calling process (monotone; bench.py reports the delta). */
 unsigned long long reyna_b200_launch_count(void);

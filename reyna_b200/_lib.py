@@ -24,7 +24,7 @@ EXPORTS = (
     "reyna_b200_boundary", "reyna_b200_compact_workspace", "reyna_b200_compact_count", "reyna_b200_compact_fill",
     "reyna_b200_mg_create", "reyna_b200_mg_destroy", "reyna_b200_mg_info", "reyna_b200_mg_apply",
     "reyna_b200_solve_workspace", "reyna_b200_solve", "reyna_b200_spmv", "reyna_b200_errors_workspace",
-    "reyna_b200_errors", "reyna_b200_evaluate", "reyna_b200_fma_probe",
+    "reyna_b200_errors", "reyna_b200_evaluate", "reyna_b200_fma_probe", "reyna_b200_dmma_probe",
     "reyna_b200_launch_count", "reyna_b200_last_error", "reyna_b200_version",
 )
 
@@ -188,6 +188,8 @@ def lib() -> C.CDLL:
     L.reyna_b200_evaluate.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp, vp]
     L.reyna_b200_fma_probe.restype = C.c_int
     L.reyna_b200_fma_probe.argtypes = [C.c_int, vp, C.POINTER(C.c_double), vp]
+    L.reyna_b200_dmma_probe.restype = C.c_int
+    L.reyna_b200_dmma_probe.argtypes = [C.c_int, vp, C.POINTER(C.c_double), vp]
     L.reyna_b200_launch_count.restype = C.c_ulonglong
     L.reyna_b200_launch_count.argtypes = []
     L.reyna_b200_last_error.restype = C.c_char_p

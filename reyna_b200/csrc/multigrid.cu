@@ -168,34 +168,62 @@ __global__ void mg_diag_inv(int n, const int32_t* __restrict__ indptr, const int
     }
 }
 
-// dense inverse of the coarsest operator: one CTA, Gauss-Jordan with partial pivoting on [A | I].  Both matrices are held
-// COLUMN-major (at[k*n + r] = A[r][k]) so that thread r sweeping over the columns k of its row is coalesced.
-__global__ void __launch_bounds__(256) mg_dense_inverse(int n, const int32_t* __restrict__ indptr,
-                                                         const int32_t* __restrict__ indices, const double* __restrict__ data,
-                                                         double* __restrict__ at, double* __restrict__ invt) {
+// dense inverse of the coarsest operator: one CTA of 1024 threads, Gauss-Jordan with partial pivoting on [A | I].  Both
+// matrices are held COLUMN-major (at[k*n + r] = A[r][k]): thread (r, slice) updates the columns k = slice, slice + 4, ... of
+// row r, coalesced over r.  The pivot is the first row with the largest magnitude (block arg-max, ties to the smaller row), so
+// the operations on every entry and their order do not depend on the thread layout.
+constexpr int kInvThreads = 1024;
+constexpr int kInvSlices = kInvThreads / kDenseMax;
+__global__ void __launch_bounds__(kInvThreads) mg_dense_inverse(int n, const int32_t* __restrict__ indptr,
+                                                                 const int32_t* __restrict__ indices, const double* __restrict__ data,
+                                                                 double* __restrict__ at, double* __restrict__ invt) {
+    __shared__ double s_best[kInvThreads / 32];
+    __shared__ int s_row[kInvThreads / 32];
     __shared__ int s_piv;
-    __shared__ double s_pv;
+    __shared__ double s_ip;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n * n; i += nt) { at[i] = 0.0; invt[i] = (i / n == i % n) ? 1.0 : 0.0; }
     __syncthreads();
     for (int r = tid; r < n; r += nt)
         for (int k = indptr[r]; k < indptr[r + 1]; ++k)
             if (indices[k] < n) at[(size_t)indices[k] * n + r] = data[k];
     __syncthreads();
+    const int row = tid % kDenseMax, slice = tid / kDenseMax;
     for (int c = 0; c < n; ++c) {
-        if (tid == 0) {
-            int piv = c;
-            double best = fabs(at[(size_t)c * n + c]);
-            for (int r = c + 1; r < n; ++r) {
-                const double v = fabs(at[(size_t)c * n + r]);
-                if (v > best) { best = v; piv = r; }
+        // pivot: first row r >= c with the largest |A[r][c]|
+        double best = -1.0;
+        int br = n;
+        for (int r = c + tid; r < n; r += nt) {
+            const double v = fabs(at[(size_t)c * n + r]);
+            if (v > best) { best = v; br = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int orow = __shfl_xor_sync(0xffffffffu, br, o);
+            if (ob > best || (ob == best && orow < br)) { best = ob; br = orow; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_row[warp] = br; }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < nt / 32 ? s_best[lane] : -1.0;
+            br = lane < nt / 32 ? s_row[lane] : n;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, br, o);
+                if (ob > best || (ob == best && orow < br)) { best = ob; br = orow; }
             }
-            s_piv = piv;
-            s_pv = at[(size_t)c * n + piv];
+            if (lane == 0) {
+                s_piv = br;
+                const double pv = at[(size_t)c * n + br];
+                s_ip = pv != 0.0 ? 1.0 / pv : 1.0;
+            }
         }
         __syncthreads();
         const int piv = s_piv;
-        const double ip = s_pv != 0.0 ? 1.0 / s_pv : 1.0;
+        const double ip = s_ip;
         // swap rows c <-> piv and scale the pivot row (thread k handles column k)
         for (int k = tid; k < n; k += nt) {
             double ac = at[(size_t)k * n + c], ap = at[(size_t)k * n + piv];
@@ -205,17 +233,20 @@ __global__ void __launch_bounds__(256) mg_dense_inverse(int n, const int32_t* __
             invt[(size_t)k * n + c] = ic * ip;
         }
         __syncthreads();
-        // eliminate column c from all other rows: thread r owns row r
-        for (int r = tid; r < n; r += nt) {
-            if (r == c) continue;
-            const double f = at[(size_t)c * n + r];
-            if (f == 0.0) continue;
-            for (int k = 0; k < n; ++k) {
-                at[(size_t)k * n + r] -= f * at[(size_t)k * n + c];
-                invt[(size_t)k * n + r] -= f * invt[(size_t)k * n + c];
+        // eliminate column c from all other rows: the multipliers are read before any slice touches column c
+        for (int r0 = 0; r0 < n; r0 += kDenseMax) {         // one pass when n <= kDenseMax (always, in practice)
+            const int r = r0 + row;
+            double f = 0.0;
+            if (r < n && r != c) f = at[(size_t)c * n + r];
+            __syncthreads();
+            if (f != 0.0) {
+                for (int k = slice; k < n; k += kInvSlices) {
+                    at[(size_t)k * n + r] -= f * at[(size_t)k * n + c];
+                    invt[(size_t)k * n + r] -= f * invt[(size_t)k * n + c];
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -616,6 +647,32 @@ __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols
         const int lo = indptr[3 * e];
         const int len = indptr[3 * e + 1] - lo;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#ifndef RB_MGB_NO_UNROLL
+        // three column slots per lane and pass (24 scalar columns = 8 blocks cover a typical row in ONE pass): all index loads,
+        // then all gathers and matrix values are in flight together; a skipped slot adds an exact fma(0, 0, s) = s, so the sums
+        // are bitwise those of the one-slot loop
+        for (int j0 = lane; j0 < len; j0 += 24) {
+            int c[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) c[u] = j0 + 8 * u < len ? indices[lo + j0 + 8 * u] : ncols;
+            double xv[3], d0[3], d1[3], d2[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const bool on = c[u] < ncols;
+                const int j = j0 + 8 * u;
+                xv[u] = on ? x[c[u]] : 0.0;
+                d0[u] = on ? (double)data[lo + j] : 0.0;
+                d1[u] = on ? (double)data[lo + len + j] : 0.0;
+                d2[u] = on ? (double)data[lo + 2 * len + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                s0 = fma(d0[u], xv[u], s0);
+                s1 = fma(d1[u], xv[u], s1);
+                s2 = fma(d2[u], xv[u], s2);
+            }
+        }
+#else
         for (int j = lane; j < len; j += 8) {
             const int c = indices[lo + j];
             if (c < ncols) {
@@ -625,6 +682,7 @@ __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols
                 s2 = fma((double)data[lo + 2 * len + j], xv, s2);
             }
         }
+#endif
 #pragma unroll
         for (int o = 4; o; o >>= 1) {
             s0 += __shfl_xor_sync(gm, s0, o, 8);
@@ -975,7 +1033,7 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
         double* scratch_a = nullptr;
         if ((rc = dev_alloc(mg, (void**)&scratch_a, sizeof(double) * (size_t)Lc.n * Lc.n))) return fail(rc);
         if ((rc = dev_alloc(mg, (void**)&mg->dense_inv, sizeof(double) * (size_t)Lc.n * Lc.n))) return fail(rc);
-        mg_dense_inverse<<<1, 256, 0, st>>>(Lc.n, Lc.indptr, Lc.indices, Lc.data, scratch_a, mg->dense_inv);
+        mg_dense_inverse<<<1, kInvThreads, 0, st>>>(Lc.n, Lc.indptr, Lc.indices, Lc.data, scratch_a, mg->dense_inv);
         if (cudaGetLastError() != cudaSuccess) { set_error("reyna_b200_mg_create: dense inverse failed"); return fail(RB_E_ARG); }
         RB_CUDA(cudaStreamSynchronize(st));
         *out = mg;
@@ -1025,7 +1083,7 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
         double* scratch_a = nullptr;
         if ((rc = dev_alloc(mg, (void**)&scratch_a, sizeof(double) * (size_t)Lc.n * Lc.n))) return fail(rc);
         if ((rc = dev_alloc(mg, (void**)&mg->dense_inv, sizeof(double) * (size_t)Lc.n * Lc.n))) return fail(rc);
-        mg_dense_inverse<<<1, 256, 0, st>>>(Lc.n, Lc.indptr, Lc.indices, Lc.data, scratch_a, mg->dense_inv);
+        mg_dense_inverse<<<1, kInvThreads, 0, st>>>(Lc.n, Lc.indptr, Lc.indices, Lc.data, scratch_a, mg->dense_inv);
         if (cudaGetLastError() != cudaSuccess) { set_error("reyna_b200_mg_create: dense inverse failed"); return fail(RB_E_ARG); }
     }
     RB_CUDA(cudaStreamSynchronize(st));

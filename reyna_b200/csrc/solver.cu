@@ -93,6 +93,51 @@ __global__ void __launch_bounds__(256) spmv_blocked_kernel(int n, const int32_t*
     }
 }
 
+// The same product with 8 lanes per BLOCK row: the D scalar rows of an element share their columns, so every x value and block
+// column is fetched once and used for D rows (the kernel above gathers it D times), and a lane keeps U column slots in flight
+// per pass.  Lane l sums the columns l, l + 8, ... of every row in increasing order and the 8 partial sums are combined by the
+// same xor tree: bitwise the result of spmv_blocked_kernel<8, D>.
+template <int D, int U>
+__global__ void __launch_bounds__(256) spmv_blockrow_kernel(int n_blk, const int32_t* __restrict__ indptr,
+                                                            const int32_t* __restrict__ bcol, const double* __restrict__ data,
+                                                            const double* __restrict__ x, double* __restrict__ y) {
+    const int lane = threadIdx.x & 7;
+    const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / 8;
+    for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8; e < n_blk; e += stride) {
+        const int lo = indptr[e * D], len = indptr[e * D + 1] - lo;
+        const int32_t* bc = bcol + lo / (D * D);
+        const double* dr = data + lo;
+        double s[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) s[r] = 0.0;
+        for (int j0 = lane; j0 < len; j0 += 8 * U) {
+            double xv[U], dv[U][D];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + 8 * u;
+                const bool on = j < len;
+                const int sb = j / D, i = j - sb * D;
+                xv[u] = on ? x[(size_t)bc[on ? sb : 0] * D + i] : 0.0;
+#pragma unroll
+                for (int r = 0; r < D; ++r) dv[u][r] = on ? dr[(size_t)r * len + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < D; ++r) s[r] = fma(dv[u][r], xv[u], s[r]);      // a skipped slot: fma(0, 0, s) = s
+        }
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int o = 4; o; o >>= 1) s[r] += __shfl_xor_sync(gm, s[r], o, 8);
+        double out = s[0];
+#pragma unroll
+        for (int r = 1; r < D; ++r) out = lane == r ? s[r] : out;
+        if (lane < D) y[e * D + lane] = out;
+    }
+}
+
 int launch_block_columns(int n_block_rows, int d, const int32_t* indptr, const int32_t* indices, int32_t* bcol,
                          cudaStream_t st) {
     block_columns_kernel<<<grid_for(n_block_rows, 256, kNumSMs * 8), 256, 0, st>>>(n_block_rows, d, indptr, indices, bcol);
@@ -105,8 +150,13 @@ static int launch_spmv_blocked(int n, int d, const int32_t* indptr, const int32_
     const int blocks_cap = kNumSMs * 16;
     const int g = grid_for((int64_t)n * 8, 256, blocks_cap);
     switch (d) {
+#ifndef RB_SPMV_ROWWISE
+        case 3: spmv_blockrow_kernel<3, 3><<<grid_for((int64_t)(n / 3) * 8, 256, blocks_cap), 256, 0, st>>>(n / 3, indptr, bcol, data, x, y); break;
+        case 6: spmv_blockrow_kernel<6, 3><<<grid_for((int64_t)(n / 6) * 8, 256, blocks_cap), 256, 0, st>>>(n / 6, indptr, bcol, data, x, y); break;
+#else
         case 3: spmv_blocked_kernel<8, 3><<<g, 256, 0, st>>>(n, indptr, bcol, data, x, y); break;
         case 6: spmv_blocked_kernel<8, 6><<<g, 256, 0, st>>>(n, indptr, bcol, data, x, y); break;
+#endif
         case 10: spmv_blocked_kernel<16, 10><<<grid_for((int64_t)n * 16, 256, blocks_cap), 256, 0, st>>>(n, indptr, bcol, data, x, y); break;
         default: return -1;
     }

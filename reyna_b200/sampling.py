@@ -41,6 +41,29 @@ def _get_pool(n: int) -> ThreadPoolExecutor:
     return _pool
 
 
+_malloc_tuned = False
+
+
+def _tune_malloc() -> None:
+    """numba returns a fresh array from every call of a compiled callable; a chunk's result is above glibc's mmap threshold, so
+    every call would mmap, page-fault and munmap its result.  ``REYNA_B200_MALLOPT=1`` raises the threshold so that the
+    per-thread arenas stay warm (12 % less evaluation time on an 8-core container, within the run-to-run noise on the 16-core
+    GPU box: opt-in, because it changes the allocator of the whole process).  Results are not affected."""
+    global _malloc_tuned
+    if _malloc_tuned:
+        return
+    _malloc_tuned = True
+    if os.environ.get("REYNA_B200_MALLOPT", "0") == "0":
+        return
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6")
+        libc.mallopt(-3, 64 * 1024 * 1024)     # M_MMAP_THRESHOLD
+        libc.mallopt(-1, 1 << 30)              # M_TRIM_THRESHOLD
+    except Exception:   # pragma: no cover  (not glibc)
+        pass
+
+
 def evaluate_batched(fn, X: np.ndarray, tail_shape: tuple, out: np.ndarray = None) -> np.ndarray:
     """``fn(X)`` for a C-contiguous (M,2) array, evaluated in chunks on the host thread pool into ``out`` (M,*tail)."""
     M = X.shape[0]
@@ -49,6 +72,7 @@ def evaluate_batched(fn, X: np.ndarray, tail_shape: tuple, out: np.ndarray = Non
     if M == 0:
         return out
     nthreads = host_threads()
+    _tune_malloc()
     if M <= _CHUNK or nthreads == 1:
         out[...] = np.asarray(fn(X), dtype=np.float64).reshape(out.shape)
         return out
@@ -70,6 +94,7 @@ def evaluate_many(terms, X: np.ndarray) -> None:
     if M == 0 or not terms:
         return
     nthreads = host_threads()
+    _tune_malloc()
     bounds = list(range(0, M, _CHUNK)) + [M]
 
     def work(i):

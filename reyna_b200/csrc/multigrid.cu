@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kInvThreads) mg_dense_inverse(int n, const int
     __shared__ int s_row[kInvThreads / 32];
     __shared__ int s_piv;
     __shared__ double s_ip;
+    __shared__ double s_prow[2 * kDenseMax];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n * n; i += nt) { at[i] = 0.0; invt[i] = (i / n == i % n) ? 1.0 : 0.0; }
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(kInvThreads) mg_dense_inverse(int n, const int
             if (piv != c) { at[(size_t)k * n + piv] = ac; invt[(size_t)k * n + piv] = ic; ac = ap; ic = ipv; }
             at[(size_t)k * n + c] = ac * ip;
             invt[(size_t)k * n + c] = ic * ip;
+            if (k < kDenseMax) { s_prow[k] = ac * ip; s_prow[kDenseMax + k] = ic * ip; }      // the scaled pivot row, for the elimination
         }
         __syncthreads();
         // eliminate column c from all other rows: the multipliers are read before any slice touches column c
@@ -240,9 +242,17 @@ __global__ void __launch_bounds__(kInvThreads) mg_dense_inverse(int n, const int
             if (r < n && r != c) f = at[(size_t)c * n + r];
             __syncthreads();
             if (f != 0.0) {
-                for (int k = slice; k < n; k += kInvSlices) {
-                    at[(size_t)k * n + r] -= f * at[(size_t)k * n + c];
-                    invt[(size_t)k * n + r] -= f * invt[(size_t)k * n + c];
+                if (n <= kDenseMax) {
+#pragma unroll 4
+                    for (int k = slice; k < n; k += kInvSlices) {
+                        at[(size_t)k * n + r] -= f * s_prow[k];
+                        invt[(size_t)k * n + r] -= f * s_prow[kDenseMax + k];
+                    }
+                } else {
+                    for (int k = slice; k < n; k += kInvSlices) {
+                        at[(size_t)k * n + r] -= f * at[(size_t)k * n + c];
+                        invt[(size_t)k * n + r] -= f * invt[(size_t)k * n + c];
+                    }
                 }
             }
             __syncthreads();
@@ -639,13 +649,40 @@ template <bool SWEEP, typename T>
 __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols, const int32_t* __restrict__ indptr,
                                                             const int32_t* __restrict__ indices, const T* __restrict__ data,
                                                             const double* __restrict__ minv, const double* __restrict__ b,
-                                                            const double* __restrict__ x, double* __restrict__ out) {
+                                                            const double* __restrict__ x, double* __restrict__ out,
+                                                            const int32_t* __restrict__ bcol) {
+    // bcol != null: one block column per 3 x 3 block (the P1 level shares the element pattern of the fine matrix) instead of
+    // one column index per scalar entry -- a third of the index bytes
     const int lane = threadIdx.x & 7;
     const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / 8;
-    for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8; e < n_blk; e += stride) {
-        const int lo = indptr[3 * e];
-        const int len = indptr[3 * e + 1] - lo;
+    int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
+    int lo_n = 0, len_n = 0;
+    if (e < n_blk) {
+        lo_n = indptr[3 * e];
+        len_n = indptr[3 * e + 1] - lo_n;
+    }
+    for (; e < n_blk; e += stride) {
+        // the dependent chain of a block row is row pointer -> column indices -> x -> tail operands: the row pointer of the NEXT
+        // row and the tail operands (b, Minv, own x) are requested up front, so only indices -> x remains serial
+        const int lo = lo_n, len = len_n;
+        if (e + stride < n_blk) {
+            lo_n = indptr[3 * (e + stride)];
+            len_n = indptr[3 * (e + stride) + 1] - lo_n;
+        }
+        double b0 = 0.0, b1 = 0.0, b2 = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0, xo = 0.0;
+#ifdef RB_MGB_LATE_TAIL
+        if (false) {
+#else
+        if (lane < 3) {
+#endif
+            b0 = b[3 * e]; b1 = b[3 * e + 1]; b2 = b[3 * e + 2];
+            if (SWEEP) {
+                const double* m = minv + 9 * (size_t)e + 3 * lane;
+                m0 = m[0]; m1 = m[1]; m2 = m[2];
+                xo = x[3 * e + lane];
+            }
+        }
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #ifndef RB_MGB_NO_UNROLL
         // three column slots per lane and pass (24 scalar columns = 8 blocks cover a typical row in ONE pass): all index loads,
@@ -654,7 +691,12 @@ __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols
         for (int j0 = lane; j0 < len; j0 += 24) {
             int c[3];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) c[u] = j0 + 8 * u < len ? indices[lo + j0 + 8 * u] : ncols;
+            for (int u = 0; u < 3; ++u) {
+                const int j = j0 + 8 * u;
+                if (j >= len) c[u] = ncols;
+                else if (bcol) c[u] = bcol[lo / 9 + j / 3] * 3 + j % 3;
+                else c[u] = indices[lo + j];
+            }
             double xv[3], d0[3], d1[3], d2[3];
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
@@ -674,7 +716,7 @@ __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols
         }
 #else
         for (int j = lane; j < len; j += 8) {
-            const int c = indices[lo + j];
+            const int c = bcol ? bcol[lo / 9 + j / 3] * 3 + j % 3 : indices[lo + j];
             if (c < ncols) {
                 const double xv = x[c];
                 s0 = fma((double)data[lo + j], xv, s0);
@@ -690,10 +732,17 @@ __global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols
             s2 += __shfl_xor_sync(gm, s2, o, 8);
         }
         if (lane < 3) {
-            const double r0 = b[3 * e] - s0, r1 = b[3 * e + 1] - s1, r2 = b[3 * e + 2] - s2;
+#ifdef RB_MGB_LATE_TAIL
+            b0 = b[3 * e]; b1 = b[3 * e + 1]; b2 = b[3 * e + 2];
             if (SWEEP) {
                 const double* m = minv + 9 * (size_t)e + 3 * lane;
-                out[3 * e + lane] = x[3 * e + lane] + fma(m[0], r0, fma(m[1], r1, m[2] * r2));
+                m0 = m[0]; m1 = m[1]; m2 = m[2];
+                xo = x[3 * e + lane];
+            }
+#endif
+            const double r0 = b0 - s0, r1 = b1 - s1, r2 = b2 - s2;
+            if (SWEEP) {
+                out[3 * e + lane] = xo + fma(m0, r0, fma(m1, r1, m2 * r2));
             } else {
                 out[3 * e + lane] = lane == 0 ? r0 : (lane == 1 ? r1 : r2);
             }
@@ -717,6 +766,7 @@ static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     const int g = mg_grid(L.n);
     const int gb = mg_grid((int64_t)L.n_blk * 8);
     const bool dist0 = (k == 0 && mg->dist != nullptr);          // partitioned level: ghost coefficients behind the owned ones
+    const int32_t* bc = (k == 0 && mg->has_p1 && !getenv("REYNA_B200_MGB_SCALAR_INDICES")) ? mg->bcol : nullptr;
     const int ncols = dist0 ? L.n + 3 * mg->n_ghost_elem : L.n;
     int rc = 0;
     // the iterate ping-pongs between L.xt and L.x; 2 nu - 1 sweeps in total, so starting in L.xt it ends in L.x
@@ -724,8 +774,8 @@ static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     mg_block_apply<false><<<g, kMgThreads, 0, st>>>(L.n, 3, L.minv, L.b, cur);
     auto sweep = [&]() {
         if (dist0 && !rc) rc = dist_halo_d(mg->dist, cur, 3, st);
-        if (L.dataf) mgb_block_row<true, float><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.dataf, L.minv, L.b, cur, oth);
-        else mgb_block_row<true, double><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth);
+        if (L.dataf) mgb_block_row<true, float><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.dataf, L.minv, L.b, cur, oth, bc);
+        else mgb_block_row<true, double><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth, bc);
         double* t = cur; cur = oth; oth = t;
     };
     for (int s = 1; s < mg->nu; ++s) sweep();
@@ -733,8 +783,8 @@ static int mgb_vcycle(rb_mg* mg, int k, cudaStream_t st) {
     MgLevel& C = mg->blev[k + 1];
     if (dist0 && !rc) rc = dist_halo_d(mg->dist, cur, 3, st);
     if (rc) return rc;
-    if (L.dataf) mgb_block_row<false, float><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.dataf, L.minv, L.b, cur, oth);
-    else mgb_block_row<false, double><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth);
+    if (L.dataf) mgb_block_row<false, float><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.dataf, L.minv, L.b, cur, oth, bc);
+    else mgb_block_row<false, double><<<gb, kMgThreads, 0, st>>>(L.n_blk, ncols, L.indptr, L.indices, L.data, L.minv, L.b, cur, oth, bc);
     if (dist0) {
         // this rank's aggregates -> slice of the global level-1 right-hand side, all-gathered; the chain below is replicated
         const int nagg_loc = (L.n_blk + 3) / 4;

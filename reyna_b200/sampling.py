@@ -28,6 +28,11 @@ def host_threads() -> int:
         n = len(os.sched_getaffinity(0))
     except Exception:   # pragma: no cover
         n = os.cpu_count() or 1
+    # one process per GPU (torchrun): the ranks of a node evaluate their callables at the same time and share its cores
+    try:
+        n //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:   # pragma: no cover
+        pass
     return max(1, min(n, 32))
 
 

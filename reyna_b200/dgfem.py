@@ -85,7 +85,7 @@ class DGFEM:
         self.device = None         # torch device; default: current CUDA device
         self.keep_device_inputs = False   # bench.py: keep the uploaded samples for kernel-only timing
         self.download_result = False      # True: dgfem() also brings B and L to (pinned) host memory, pipelined with the assembly
-        self.pipeline_chunk_elements = 131072   # elements per evaluate/upload/assemble/download pipeline stage
+        self.pipeline_chunk_elements = 65536    # elements per evaluate/upload/assemble/download pipeline stage
         self._host = None                 # host copy of the last system (download_result)
         self._inputs = None
         self._side_streams = {}
@@ -227,30 +227,61 @@ class DGFEM:
             self._pinned[key] = buf
         return buf
 
-    def _put(self, torch, dev, dev_t, key, fn, X, tail) -> int:
-        """Evaluate ``fn`` on all of ``X`` into pinned memory and start the upload; returns the bytes uploaded."""
+    def _put(self, torch, pending, key, fn, X, tail) -> None:
+        """Queue the evaluation of ``fn`` on all of ``X`` into pinned memory (host thread pool); ``_upload_pending`` waits for it
+        and starts the upload."""
         M = X.shape[0]
         if M == 0:
-            return 0
+            return
         # one spare row: the volume kernel's bulk copies move 16-byte units (rb_coefs, include/reyna_b200.h)
         buf = self._staging(torch, key, (M + 1,) + tail)
-        sampling.evaluate_batched(fn, X, tail, out=buf.numpy()[:M])
-        buf.numpy()[M] = 0.0
-        dev_t[key] = buf.to(dev, non_blocking=True)[:M]
-        return M * int(np.prod(tail, dtype=np.int64)) * 8
+        job = sampling.submit_terms([(fn, tail, buf.numpy()[:M])], X)
+        pending.append((key, buf, M, tail, job))
 
-    def _sample_face_coefficients(self, torch, dev, fg, pts):
+    @staticmethod
+    def _upload_pending(dev, dev_t, pending) -> int:
+        """Wait for the queued evaluations in order and start their uploads; returns the bytes uploaded."""
+        nbytes = 0
+        for key, buf, M, tail, job in pending:
+            job.wait()
+            buf.numpy()[M] = 0.0
+            dev_t[key] = buf.to(dev, non_blocking=True)[:M]
+            nbytes += M * int(np.prod(tail, dtype=np.int64)) * 8
+        return nbytes
+
+    def _submit_face_coefficients(self, torch, fg, pts):
+        """Queue the evaluation of the interior-face and boundary-face samples (q-major) on the host thread pool."""
+        pending = []
+        b_mid = b_job = None
+        if fg.n_iface:
+            mid, Xf = pts['mid_i'], pts['Xi']
+            if self.advection is not None:
+                # first in the queue: the upwind flags (structure) are the first thing the device needs
+                b_mid = np.empty((mid.shape[0], 2), dtype=np.float64)
+                b_job = sampling.submit_terms([(self.advection, (2,), b_mid)], mid)
+            if self.diffusion is not None:
+                self._put(torch, pending, 'if_a', self.diffusion, Xf, (2, 2))
+                self._put(torch, pending, 'if_a_mid', self.diffusion, mid, (2, 2))
+            if self.advection is not None:
+                self._put(torch, pending, 'if_b', self.advection, Xf, (2,))
+        if fg.n_bface:
+            mid, Xb = pts['mid_b'], pts['Xb']
+            self._put(torch, pending, 'bf_g', self.dirichlet_bcs, Xb, ())
+            if self.diffusion is not None:
+                self._put(torch, pending, 'bf_a', self.diffusion, Xb, (2, 2))
+                self._put(torch, pending, 'bf_a_mid', self.diffusion, mid, (2, 2))
+            if self.advection is not None:
+                self._put(torch, pending, 'bf_b', self.advection, Xb, (2,))
+        return pending, b_mid, b_job
+
+    def _sample_face_coefficients(self, torch, dev, fg, pts, submitted=None):
         """Interior-face and boundary-face samples (q-major) + upwind flags: everything the structure and the prepass need."""
+        pending, b_mid, b_job = submitted if submitted is not None else self._submit_face_coefficients(torch, fg, pts)
         dev_t, nbytes = {}, 0
         self._upwind_host = None
         if fg.n_iface:
-            mid, Xf = pts['mid_i'], pts['Xi']
-            if self.diffusion is not None:
-                nbytes += self._put(torch, dev, dev_t, 'if_a', self.diffusion, Xf, (2, 2))
-                nbytes += self._put(torch, dev, dev_t, 'if_a_mid', self.diffusion, mid, (2, 2))
             if self.advection is not None:
-                nbytes += self._put(torch, dev, dev_t, 'if_b', self.advection, Xf, (2,))
-                b_mid = sampling.evaluate_batched(self.advection, mid, (2,))
+                b_job.wait()
                 # b(mid) . n >= 1e-12 (full_assembly.py:194); written out per component: np.sum(.., axis=1) over two columns
                 # costs 25 ns per face on one core (75 ms at 3 M faces), the same two products and one add cost 3 ns
                 upw = ((b_mid[:, 0] * fg.inorm[:, 0] + b_mid[:, 1] * fg.inorm[:, 1]) >= 1e-12).astype(np.uint8)
@@ -260,14 +291,7 @@ class DGFEM:
         elif self.advection is not None:
             dev_t['if_upwind'] = torch.zeros(1, dtype=torch.uint8, device=dev)     # no interior face: nothing to flag
             self._upwind_host = np.zeros(0, dtype=np.uint8)
-        if fg.n_bface:
-            mid, Xb = pts['mid_b'], pts['Xb']
-            nbytes += self._put(torch, dev, dev_t, 'bf_g', self.dirichlet_bcs, Xb, ())
-            if self.diffusion is not None:
-                nbytes += self._put(torch, dev, dev_t, 'bf_a', self.diffusion, Xb, (2, 2))
-                nbytes += self._put(torch, dev, dev_t, 'bf_a_mid', self.diffusion, mid, (2, 2))
-            if self.advection is not None:
-                nbytes += self._put(torch, dev, dev_t, 'bf_b', self.advection, Xb, (2,))
+        nbytes += self._upload_pending(dev, dev_t, pending)
         return dev_t, nbytes
 
     def _volume_terms(self):
@@ -406,7 +430,21 @@ class DGFEM:
 
             t1 = time.perf_counter()
             pts = sampling.cached_points(self._geo, fg, self.element_reference_quadrature, self.edge_reference_quadrature)
-            cd, nbytes = self._sample_face_coefficients(torch, dev, fg, pts)
+            # ALL evaluations of the call are queued on the host thread pool now -- face samples first, then the volume samples
+            # chunk by chunk -- and consumed in that order below: the host threads never idle at a barrier between the stages
+            face_jobs = self._submit_face_coefficients(torch, fg, pts)
+            Xs = pts['Xs']
+            M = Xs.shape[0]
+            terms = self._volume_terms()
+            Q = int(np.asarray(self.element_reference_quadrature[1]).shape[0])
+            chunks = self._chunks(fg, vs)
+            bufs = [self._staging(torch, key, (M + 1,) + tail) for key, _, tail in terms]
+            vol_jobs = []
+            for (_, _, r_lo, r_hi) in chunks:
+                lo, hi = Q * int(vs.vround_tri0[r_lo]), Q * int(vs.vround_tri0[r_hi])
+                vol_jobs.append((lo, hi, sampling.submit_terms([(fn, tail, buf.numpy()) for (_, fn, tail), buf in zip(terms, bufs)],
+                                                               Xs, lo, hi)))
+            cd, nbytes = self._sample_face_coefficients(torch, dev, fg, pts, submitted=face_jobs)
             flags, bnd_elem, bnd_off, bnd_face = self._boundary_lists(fg)
             bd = {k: torch.from_numpy(v).to(dev) for k, v in
                   dict(flags=flags, bnd_elem=bnd_elem, bnd_off=bnd_off, bnd_face=bnd_face).items()}
@@ -415,9 +453,6 @@ class DGFEM:
             tm['face_eval_upload_s'] = time.perf_counter() - t1
 
             # volume samples: device arrays now (the kernels get their final addresses), contents chunk by chunk below
-            Xs = pts['Xs']
-            M = Xs.shape[0]
-            terms = self._volume_terms()
             for key, _, tail in terms:
                 cd[key] = torch.empty((M + 1,) + tail, dtype=torch.float64, device=dev)[:M]
                 nbytes += M * int(np.prod(tail, dtype=np.int64)) * 8
@@ -425,14 +460,10 @@ class DGFEM:
 
             ctx = self._begin_on_device(torch, L, dev, sp, fg, gd, cd, tm)
             self._start_index_download(torch, ctx)
-            Q = int(np.asarray(self.element_reference_quadrature[1]).shape[0])
             s_in = self._stream(torch, dev, 'h2d')
             t2 = time.perf_counter()
-            for (e_lo, e_hi, r_lo, r_hi) in self._chunks(fg, vs):
-                lo, hi = Q * int(vs.vround_tri0[r_lo]), Q * int(vs.vround_tri0[r_hi])
-                bufs = [self._staging(torch, key, (M + 1,) + tail) for key, _, tail in terms]
-                # all callables on a block of points while it is cache-resident
-                sampling.evaluate_many([(fn, tail, buf.numpy()[lo:hi]) for (key, fn, tail), buf in zip(terms, bufs)], Xs[lo:hi])
+            for (e_lo, e_hi, r_lo, r_hi), (lo, hi, job) in zip(chunks, vol_jobs):
+                job.wait()
                 with torch.cuda.stream(s_in):
                     for (key, _, _), buf in zip(terms, bufs):
                         cd[key][lo:hi].copy_(buf[lo:hi], non_blocking=True)

@@ -91,6 +91,46 @@ def evaluate_batched(fn, X: np.ndarray, tail_shape: tuple, out: np.ndarray = Non
     return out
 
 
+class EvalJob:
+    """Pending evaluation of some callables over a range of points (``submit_terms``): ``wait()`` returns when every task has
+    written its rows and re-raises the first exception a callable threw."""
+
+    def __init__(self, futures):
+        self._futures = futures
+
+    def wait(self) -> None:
+        for f in self._futures:
+            f.result()
+        self._futures = ()
+
+
+def submit_terms(terms, X: np.ndarray, lo: int = 0, hi: int = None) -> EvalJob:
+    """Queue ``out[lo:hi] = fn(X[lo:hi])`` for every ``(fn, tail_shape, out)`` of ``terms`` on the host thread pool and return at
+    once.  The range is cut into tasks of at most ``_CHUNK`` points; a task applies ALL callables to its points while they are
+    cache-resident.  Jobs are served in submission order, so a caller that submits the jobs of a whole assembly up front and
+    then waits for them one by one keeps every host thread busy from the first face sample to the last volume sample -- there
+    is no barrier at which threads idle (bit-identical to ``evaluate_batched``: element-wise functions)."""
+    hi = X.shape[0] if hi is None else hi
+    M = hi - lo
+    if M <= 0 or not terms:
+        return EvalJob(())
+    nthreads = host_threads()
+    _tune_malloc()
+
+    def work(a, b):
+        Xc = X[a:b]
+        for fn, tail, out in terms:
+            out[a:b] = np.asarray(fn(Xc), dtype=np.float64).reshape((b - a,) + tuple(tail))
+
+    if nthreads == 1 or M <= _CHUNK // 4:
+        work(lo, hi)                      # not worth a hand-off
+        return EvalJob(())
+    ntask = -(-M // _CHUNK)
+    step = -(-M // ntask)
+    pool = _get_pool(nthreads)
+    return EvalJob([pool.submit(work, a, min(a + step, hi)) for a in range(lo, hi, step)])
+
+
 def evaluate_many(terms, X: np.ndarray) -> None:
     """``out[...] = fn(X)`` for every ``(fn, tail_shape, out)`` of ``terms``, chunk by chunk on the host thread pool with ALL
     callables applied to a chunk of points while it is cache-resident (the point array is read from memory once instead of

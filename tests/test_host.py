@@ -177,6 +177,38 @@ def test_batched_sampling_is_chunk_invariant(monkeypatch):
     assert np.array_equal(per_item, whole_f[:900])
 
 
+def test_submitted_jobs_equal_batched_evaluation(monkeypatch):
+    """submit_terms (jobs queued up front on the thread pool, consumed in order: the dgfem() pipeline) writes bit for bit
+    what evaluate_batched writes, for ranges, several callables per task and a callable that raises."""
+    from numba import njit, f8
+    f = njit(f8[:](f8[:, :]), nogil=True)(PROBLEMS["adr"]["data"]["forcing"])
+    a = njit(f8[:, :, :](f8[:, :]), nogil=True)(PROBLEMS["variable"]["data"]["diffusion"])
+    X = np.random.default_rng(5).random((9001, 2))
+    monkeypatch.setattr(sampling, "_CHUNK", 1 << 30)
+    whole_f, whole_a = sampling.evaluate_batched(f, X, ()), sampling.evaluate_batched(a, X, (2, 2))
+    monkeypatch.setattr(sampling, "_CHUNK", 640)
+    monkeypatch.setenv("REYNA_B200_HOST_THREADS", "3")
+    out_f, out_a = np.full(9001, np.nan), np.full((9001, 2, 2), np.nan)
+    jobs = [sampling.submit_terms([(f, (), out_f), (a, (2, 2), out_a)], X, lo, hi) for lo, hi in ((0, 4000), (4000, 4100), (4100, 9001))]
+    for j in jobs:
+        j.wait()
+    assert np.array_equal(out_f, whole_f) and np.array_equal(out_a, whole_a)
+    assert sampling.submit_terms([(f, (), out_f)], X, 10, 10)._futures == ()      # empty range
+
+    def bad(x):
+        raise RuntimeError("callable failed")
+    with pytest.raises(RuntimeError, match="callable failed"):
+        sampling.submit_terms([(bad, (), out_f)], X).wait()
+
+
+def test_host_threads_are_shared_between_the_ranks_of_a_node(monkeypatch):
+    monkeypatch.delenv("REYNA_B200_HOST_THREADS", raising=False)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    n1 = sampling.host_threads()
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    assert sampling.host_threads() == max(1, min(32, len(__import__("os").sched_getaffinity(0)) // 2)) <= n1
+
+
 def test_sampling_points_match_oracle_layout():
     from oracle import dg_oracle
     g = rb.DGFEMGeometry(rb.voronoi_mesh(40, seed=6))

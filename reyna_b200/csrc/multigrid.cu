@@ -69,7 +69,10 @@ struct rb_mg {
     rb_dist* dist = nullptr;
     int n_ghost_elem = 0, lo_elem = 0;
     std::vector<int32_t> bounds, bounds_l1;
-    std::vector<void*> owned;
+    std::vector<void*> owned;      // arena chunks (cudaMalloc), released by reyna_b200_mg_destroy
+    char* arena_cur = nullptr;     // the hierarchy sub-allocates its ~100 arrays from a few large chunks: cudaMalloc costs
+    size_t arena_left = 0;         // 0.1 ... 10 ms per call on a busy driver, which used to dominate the set-up of small solves
+    size_t arena_chunk = 8u << 20;
     // agglomerated-P1 chain (rb_mg_opts.elem_bbox given): blev[0] is the P1 level itself
     int agg_p1 = 0, nblev = 0;
     rb::MgLevel blev[rb::kMaxLevels];
@@ -78,8 +81,19 @@ struct rb_mg {
 namespace rb {
 
 static int dev_alloc(rb_mg* mg, void** ptr, size_t bytes) {
-    RB_CUDA(cudaMalloc(ptr, bytes > 0 ? bytes : 16));
-    mg->owned.push_back(*ptr);
+    bytes = (bytes + 255) & ~(size_t)255;        // cudaMalloc's alignment
+    if (bytes == 0) bytes = 256;
+    if (bytes > mg->arena_left) {
+        const size_t chunk = bytes > mg->arena_chunk ? bytes : mg->arena_chunk;
+        void* p = nullptr;
+        RB_CUDA(cudaMalloc(&p, chunk));
+        mg->owned.push_back(p);
+        mg->arena_cur = static_cast<char*>(p);
+        mg->arena_left = chunk;
+    }
+    *ptr = mg->arena_cur;
+    mg->arena_cur += bytes;
+    mg->arena_left -= bytes;
     return 0;
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -645,8 +659,11 @@ static int mg_vcycle(rb_mg* mg, int k, cudaStream_t st) {
 // every x value is gathered once and used for the three rows.  SWEEP == false: out = b - A x;  SWEEP == true: the damped block
 // Jacobi update out = x + Minv (b - A x) (omega folded into minv), written to another buffer than x.  Columns >= ncols are
 // ghost couplings the level ignores.  Fixed shuffle tree: deterministic.
+#ifndef RB_MGB_MINB
+#define RB_MGB_MINB 1
+#endif
 template <bool SWEEP, typename T>
-__global__ void __launch_bounds__(kMgThreads) mgb_block_row(int n_blk, int ncols, const int32_t* __restrict__ indptr,
+__global__ void __launch_bounds__(kMgThreads, RB_MGB_MINB) mgb_block_row(int n_blk, int ncols, const int32_t* __restrict__ indptr,
                                                             const int32_t* __restrict__ indices, const T* __restrict__ data,
                                                             const double* __restrict__ minv, const double* __restrict__ b,
                                                             const double* __restrict__ x, double* __restrict__ out,
@@ -938,6 +955,12 @@ extern "C" int reyna_b200_mg_create(int32_t n, int32_t d, int32_t p, const int32
     RB_CUDA(cudaStreamSynchronize(st));
     const int64_t nnz_f = h_last;
     const int64_t nblocks = nnz_f / ((int64_t)d * d);
+    {   // arena chunks of about the size of the P1 level (the largest thing the hierarchy owns): 8 MB ... 2 GB
+        size_t chunk = (size_t)nnz_f * 4;
+        if (chunk < (8u << 20)) chunk = 8u << 20;
+        if (chunk > ((size_t)2 << 30)) chunk = (size_t)2 << 30;
+        mg->arena_chunk = chunk;
+    }
 
     // ---- P1 level --------------------------------------------------------------------------------------------------
     MgLevel& L0 = mg->lev[0];

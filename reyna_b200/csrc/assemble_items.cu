@@ -132,14 +132,16 @@ struct VolSmem {
     static constexpr int SAMPLES = END1, H1B = END1 - END0;
     static constexpr int PARTB = DM::NPAIR_MAX * kPartStride * 16;
     // one part (RS == 1): the partial blocks are reduced through the consumed half 1, in NPASS passes of PP value pairs;
-    // several parts: the samples have to survive, the partials get a buffer of their own
-    static constexpr int NPASS = RS == 1 ? (PARTB + H1B - 1) / H1B : 1;
+    // several parts: the samples have to survive, the partials get a buffer of their own -- a small one, walked in five
+    // passes, so that six one-warp CTAs fit an SM at p = 3 (a buffer for all pairs at once: 49 KB per CTA, four CTAs)
+    static constexpr int NPASS = RS == 1 ? (PARTB + H1B - 1) / H1B : 5;
     static constexpr int PP = (DM::NPAIR_MAX + NPASS - 1) / NPASS;
+    static constexpr int PBUF = PP * kPartStride * 16;
     static constexpr int OPART = RS == 1 ? END0 : SAMPLES;
-    static constexpr int OMETA = (RS == 1 ? SAMPLES : SAMPLES + PARTB);       // int s_start[36], s_seg[36]
+    static constexpr int OMETA = (RS == 1 ? SAMPLES : SAMPLES + PBUF);        // int s_start[36], s_seg[36]
     static constexpr int OBAR = OMETA + 4 * 72;
     static constexpr int TOTAL = OBAR + 16;
-    static_assert(PP * kPartStride * 16 <= (RS == 1 ? H1B : PARTB), "partial buffer");
+    static_assert(PP * kPartStride * 16 <= (RS == 1 ? H1B : PBUF), "partial buffer");
     static_assert(END0 % 16 == 0 && OMETA % 16 == 0, "alignment");
 };
 
@@ -1159,7 +1161,15 @@ static int launch(const AsmArgs& A, cudaStream_t st, int phases) {
     if ((phases & 1) && A.vround_hi > A.vround_lo) {
         const int nrounds = A.vround_hi - A.vround_lo;
         RB_CUDA(cudaMemsetAsync(A.vol_next, 0, sizeof(int), st));
-        vk<<<nrounds < kVolWarps ? nrounds : kVolWarps, kWarp, VS::TOTAL, st>>>(A);
+        // persistent warps: exactly as many one-warp CTAs as are resident at once (11 per SM at p <= 2, 6 at p = 3)
+        static int resident = 0;
+        if (resident == 0) {
+            int per_sm = 0;
+            RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vk, kWarp, VS::TOTAL));
+            resident = kNumSMs * (per_sm > 0 ? per_sm : 1);
+            if (resident > kVolWarps) resident = kVolWarps;
+        }
+        vk<<<nrounds < resident ? nrounds : resident, kWarp, VS::TOTAL, st>>>(A);
         RB_LAUNCH_CHECK("dg_volume_kernel");
     }
     if (!(phases & 2)) return 0;

@@ -444,35 +444,42 @@ class DGFEM:
                 lo, hi = Q * int(vs.vround_tri0[r_lo]), Q * int(vs.vround_tri0[r_hi])
                 vol_jobs.append((lo, hi, sampling.submit_terms([(fn, tail, buf.numpy()) for (_, fn, tail), buf in zip(terms, bufs)],
                                                                Xs, lo, hi)))
-            cd, nbytes = self._sample_face_coefficients(torch, dev, fg, pts, submitted=face_jobs)
-            flags, bnd_elem, bnd_off, bnd_face = self._boundary_lists(fg)
-            bd = {k: torch.from_numpy(v).to(dev) for k, v in
-                  dict(flags=flags, bnd_elem=bnd_elem, bnd_off=bnd_off, bnd_face=bnd_face).items()}
-            bd['has_spill'] = bool((flags & 4).any())
-            bd['bnd_elem_host'] = bnd_elem
-            tm['face_eval_upload_s'] = time.perf_counter() - t1
+            try:
+                cd, nbytes = self._sample_face_coefficients(torch, dev, fg, pts, submitted=face_jobs)
+                flags, bnd_elem, bnd_off, bnd_face = self._boundary_lists(fg)
+                bd = {k: torch.from_numpy(v).to(dev) for k, v in
+                      dict(flags=flags, bnd_elem=bnd_elem, bnd_off=bnd_off, bnd_face=bnd_face).items()}
+                bd['has_spill'] = bool((flags & 4).any())
+                bd['bnd_elem_host'] = bnd_elem
+                tm['face_eval_upload_s'] = time.perf_counter() - t1
 
-            # volume samples: device arrays now (the kernels get their final addresses), contents chunk by chunk below
-            for key, _, tail in terms:
-                cd[key] = torch.empty((M + 1,) + tail, dtype=torch.float64, device=dev)[:M]
-                nbytes += M * int(np.prod(tail, dtype=np.int64)) * 8
-            tm['h2d_bytes'] = int(nbytes)
+                # volume samples: device arrays now (the kernels get their final addresses), contents chunk by chunk below
+                for key, _, tail in terms:
+                    cd[key] = torch.empty((M + 1,) + tail, dtype=torch.float64, device=dev)[:M]
+                    nbytes += M * int(np.prod(tail, dtype=np.int64)) * 8
+                tm['h2d_bytes'] = int(nbytes)
 
-            ctx = self._begin_on_device(torch, L, dev, sp, fg, gd, cd, tm)
-            self._start_index_download(torch, ctx)
-            s_in = self._stream(torch, dev, 'h2d')
-            t2 = time.perf_counter()
-            for (e_lo, e_hi, r_lo, r_hi), (lo, hi, job) in zip(chunks, vol_jobs):
-                job.wait()
-                with torch.cuda.stream(s_in):
-                    for (key, _, _), buf in zip(terms, bufs):
-                        cd[key][lo:hi].copy_(buf[lo:hi], non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record(s_in)
-                stream.wait_event(ready)
-                self._assemble_chunk(torch, L, sp, ctx, bd, e_lo, e_hi, r_lo, r_hi)
-                self._start_rows_download(torch, ctx, e_lo, e_hi)
-            tm['volume_eval_pipeline_s'] = time.perf_counter() - t2
+                ctx = self._begin_on_device(torch, L, dev, sp, fg, gd, cd, tm)
+                self._start_index_download(torch, ctx)
+                s_in = self._stream(torch, dev, 'h2d')
+                t2 = time.perf_counter()
+                for (e_lo, e_hi, r_lo, r_hi), (lo, hi, job) in zip(chunks, vol_jobs):
+                    job.wait()
+                    with torch.cuda.stream(s_in):
+                        for (key, _, _), buf in zip(terms, bufs):
+                            cd[key][lo:hi].copy_(buf[lo:hi], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(s_in)
+                    stream.wait_event(ready)
+                    self._assemble_chunk(torch, L, sp, ctx, bd, e_lo, e_hi, r_lo, r_hi)
+                    self._start_rows_download(torch, ctx, e_lo, e_hi)
+                tm['volume_eval_pipeline_s'] = time.perf_counter() - t2
+            except BaseException:
+                # a callable or a launch failed: no queued task may still be writing into the (cached) staging buffers
+                for job in [face_jobs[2]] + [j for _, _, _, _, j in face_jobs[0]] + [j for _, _, j in vol_jobs]:
+                    if job is not None:
+                        job.abandon()
+                raise
             self._dev = self._finish_on_device(torch, L, dev, sp, fg, gd, ctx, bd, tm)
             self._inputs = (fg, gd, cd, bd) if self.keep_device_inputs else None
             stream.synchronize()

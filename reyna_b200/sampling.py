@@ -103,6 +103,18 @@ class EvalJob:
             f.result()
         self._futures = ()
 
+    def abandon(self) -> None:
+        """Drop the job after a failure elsewhere: tasks that have not started are cancelled, running ones are waited for (they
+        write into buffers the next call reuses); their own exceptions are swallowed."""
+        for f in self._futures:
+            f.cancel()
+        for f in self._futures:
+            try:
+                f.result()
+            except BaseException:      # noqa: BLE001 - includes CancelledError
+                pass
+        self._futures = ()
+
 
 def submit_terms(terms, X: np.ndarray, lo: int = 0, hi: int = None) -> EvalJob:
     """Queue ``out[lo:hi] = fn(X[lo:hi])`` for every ``(fn, tail_shape, out)`` of ``terms`` on the host thread pool and return at

@@ -199,6 +199,11 @@ def test_submitted_jobs_equal_batched_evaluation(monkeypatch):
         raise RuntimeError("callable failed")
     with pytest.raises(RuntimeError, match="callable failed"):
         sampling.submit_terms([(bad, (), out_f)], X).wait()
+    # after a failure the other jobs of the call are abandoned: cancelled or finished, never left running, no exception
+    rest = [sampling.submit_terms([(bad, (), out_f)], X), sampling.submit_terms([(f, (), out_f)], X)]
+    for j in rest:
+        j.abandon()
+    assert all(j._futures == () for j in rest)
 
 
 def test_host_threads_are_shared_between_the_ranks_of_a_node(monkeypatch):

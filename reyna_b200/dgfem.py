@@ -85,7 +85,8 @@ class DGFEM:
         self.device = None         # torch device; default: current CUDA device
         self.keep_device_inputs = False   # bench.py: keep the uploaded samples for kernel-only timing
         self.download_result = False      # True: dgfem() also brings B and L to (pinned) host memory, pipelined with the assembly
-        self.pipeline_chunk_elements = 65536    # elements per evaluate/upload/assemble/download pipeline stage
+        # elements per evaluate/upload/assemble/download pipeline stage
+        self.pipeline_chunk_elements = int(os.environ.get('REYNA_B200_PIPELINE_CHUNK', 65536))
         self._host = None                 # host copy of the last system (download_result)
         self._inputs = None
         self._side_streams = {}

@@ -481,10 +481,14 @@ class DGFEM:
                     if job is not None:
                         job.abandon()
                 raise
+            t3 = time.perf_counter()
             self._dev = self._finish_on_device(torch, L, dev, sp, fg, gd, ctx, bd, tm)
             self._inputs = (fg, gd, cd, bd) if self.keep_device_inputs else None
             stream.synchronize()
+            tm['device_tail_s'] = time.perf_counter() - t3          # last chunk's upload + kernels after its evaluation
+            t4 = time.perf_counter()
             self._finish_download(torch, ctx, tm)
+            tm['download_tail_s'] = time.perf_counter() - t4        # what is left of the D2H when the device is done
         tm['assemble_total_s'] = time.perf_counter() - t0
 
     def _stream(self, torch, dev, name):
